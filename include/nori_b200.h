@@ -1,0 +1,161 @@
+/*
+ * nori_b200.h -- C-ABI of the Blackwell-native render hot path for Nori (libnori_b200.so).
+ *
+ * The reference (wjakob/nori @ 092f581) has NO FFI: plugins are translation units linked
+ * into one executable (ref: CMakeLists.txt:40-91, include/nori/object.h:141-149).  The
+ * boundary below is therefore defined by the three seams of the reference's own host code
+ * that the GPU path replaces; each entry point cites the reference
+ * interface it stands in for.  Plain C: pointers and sizes only, no C++/torch types, no
+ * exceptions, no callbacks.  Every int-returning function returns 0 on success and
+ * nonzero on failure with a thread-local message in nb_last_error() -- the host wrapper
+ * rethrows it as NoriException (ref: include/nori/common.h:135-140).
+ *
+ * Threading: one nb_ctx is driven by one host thread at a time (the reference's render
+ * thread, ref: src/main.cpp:78).  There is no CPU fallback anywhere behind this API:
+ * nb_create fails if no CUDA device is usable, and unsupported plugin types are errors.
+ */
+#ifndef NORI_B200_H
+#define NORI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_ABI_VERSION 1
+#define NB_BLOCK_SIZE 32          /* ref: include/nori/block.h:17  NORI_BLOCK_SIZE */
+#define NB_FILTER_RESOLUTION 32   /* ref: include/nori/rfilter.h:12 */
+#define NB_MISS 0xffffffffu
+
+/* BSDF plugins the device path knows (ref: src/diffuse.cpp, src/mirror.cpp, src/dielectric.cpp, src/microfacet.cpp) */
+enum { NB_BSDF_DIFFUSE = 0, NB_BSDF_MIRROR = 1, NB_BSDF_DIELECTRIC = 2, NB_BSDF_MICROFACET = 3 };
+/* Emitter plugins (interface ref: include/nori/emitter.h:16-24; "area" is authored) */
+enum { NB_EMITTER_NONE = 0, NB_EMITTER_AREA = 1 };
+/* Integrator plugins named by the shipped scenes (ref: scenes/pa1/bunny.xml:8, pa3/ajax-ao.xml:8,
+ * pa4/cbox/cbox-whitted.xml:4, pa5/cbox/cbox_{mats,ems,mis}.xml:4); interface ref: include/nori/integrator.h:42 */
+enum { NB_INT_NORMALS = 0, NB_INT_AO = 1, NB_INT_WHITTED = 2, NB_INT_PATH_MATS = 3, NB_INT_PATH_EMS = 4, NB_INT_PATH_MIS = 5 };
+/* Sampler stream assignment.  PER_BLOCK is the reference's Independent::prepare (ref: src/independent.cpp:36-41):
+ * one sequential pcg32 stream per 32x32 block.  PER_SAMPLE seeds one stream per (pixel, sample) through the
+ * generate()/advance() hooks of the Sampler API (ref: include/nori/sampler.h:66-83) and is the parallel-friendly mode. */
+enum { NB_SEED_PER_SAMPLE = 0, NB_SEED_PER_BLOCK = 1 };
+
+typedef struct nb_bsdf_desc {
+    int32_t type;
+    float   albedo[3];      /* Diffuse "albedo" (ref: src/diffuse.cpp:19) / Microfacet "kd" (ref: src/microfacet.cpp:27) */
+    float   alpha;          /* Microfacet "alpha" (ref: src/microfacet.cpp:18) */
+    float   intIOR, extIOR; /* ref: src/microfacet.cpp:21-24, src/dielectric.cpp:17-20 */
+    float   ks;             /* 1 - max(kd) (ref: src/microfacet.cpp:36) */
+} nb_bsdf_desc;
+
+typedef struct nb_emitter_desc {
+    int32_t type;
+    float   radiance[3];
+} nb_emitter_desc;
+
+typedef struct nb_integrator_desc {
+    int32_t type;
+    int32_t rr_start;   /* first bounce index at which Russian roulette applies (path_*); <=0 -> 3 */
+    int32_t max_depth;  /* cap on path vertices; <=0 -> 1<<20 */
+    int32_t reserved;
+} nb_integrator_desc;
+
+/* Batched equivalent of the arguments of Accel::rayIntersect (ref: include/nori/accel.h:54, include/nori/ray.h:30-34) */
+typedef struct nb_ray { float o[3]; float mint; float d[3]; float maxt; } nb_ray;     /* 32 B */
+typedef struct nb_hit { float t, u, v; uint32_t prim; uint32_t mesh; } nb_hit;        /* 20 B; prim = global triangle index, NB_MISS = none */
+
+typedef struct nb_stats {
+    uint64_t samples;       /* camera samples rendered by this context (its tiles only) */
+    uint64_t rays;          /* camera + extension + shadow rays traced (device counter) */
+    uint64_t node_visits;   /* BVH node visits (device counter) */
+    uint64_t tri_tests;     /* ray/triangle tests (device counter) */
+    uint64_t hits_shaded;   /* closest hits for which an intersection record was filled */
+    double   kernel_ms;     /* device time of the render kernel(s) of the last nb_render*, CUDA events on the launch stream */
+    double   total_ms;      /* device time of the whole last nb_render* call incl. clears, merge and copies */
+    uint64_t launches;      /* kernels launched by the last call */
+    uint64_t h2d_bytes, d2h_bytes;  /* bytes copied by the last call */
+} nb_stats;
+
+typedef struct nb_ctx nb_ctx;
+
+/* Context owns all device memory and streams for ONE device.  device < 0 selects the current device.
+ * Replaces: the Accel instance a Scene owns (ref: src/scene.cpp:16-18). */
+nb_ctx *nb_create(int device);
+void    nb_destroy(nb_ctx *);
+const char *nb_last_error(void);
+int     nb_abi_version(void);
+
+/* Replaces Accel::addMesh (ref: src/accel.cpp:12-17; called from Scene::addChild, ref: src/scene.cpp:48-53).
+ * V: 3*nv floats packed xyz == m_V 3xN column-major (ref: include/nori/mesh.h:160); N (3*nv) and UV (2*nv)
+ * nullable; F: 3*nf uint32 == m_F.  Caller keeps ownership, callee copies.  Lifts the single-mesh
+ * limit (ref: src/accel.cpp:13-14).  bsdf NULL -> default diffuse 0.5 (ref: src/mesh.cpp:23-29).
+ * Returns the mesh id (>=0) or -1. */
+int nb_add_mesh(nb_ctx *, const float *V, uint32_t nv, const float *N, const float *UV,
+                const uint32_t *F, uint32_t nf, const nb_bsdf_desc *bsdf, const nb_emitter_desc *emitter);
+int nb_clear_meshes(nb_ctx *);
+
+/* Replaces Accel::build (ref: src/accel.cpp:19-21; called from Scene::activate, ref: src/scene.cpp:28):
+ * host SAH BVH build + SoA upload. */
+int nb_build_accel(nb_ctx *);
+/* Re-uploads the already built scene arrays from pinned host memory (used to time host->device traffic). */
+int nb_upload_scene(nb_ctx *);
+
+/* PerspectiveCamera state (ref: src/perspective.cpp:22-39,41-68): row-major 4x4 sampleToCamera and
+ * cameraToWorld, output size, clip planes.  Ray generation follows ref: src/perspective.cpp:76-97. */
+int nb_set_camera(nb_ctx *, const float s2c[16], const float c2w[16], int width, int height, float nearClip, float farClip);
+
+/* Reconstruction filter as ImageBlock tabulates it (ref: src/block.cpp:19-27): table[i] = filter->eval(radius*i/32),
+ * table[32] = 0, evaluated by the HOST plugin so any ReconstructionFilter plugin works unchanged. */
+int nb_set_filter(nb_ctx *, const float table[NB_FILTER_RESOLUTION + 1], float radius);
+
+/* Sampler state (ref: src/independent.cpp:23-25 "sampleCount"). */
+int nb_set_sampler(nb_ctx *, uint32_t spp, int seed_mode, uint64_t seed);
+
+/* Integrator selection; unsupported type -> error (no CPU fallback). */
+int nb_set_integrator(nb_ctx *, const nb_integrator_desc *);
+
+/* Tile sharding across GPUs: this context renders only 32x32 tiles with tile_id % nranks == rank
+ * (tile_id = by * ceil(W/32) + bx).  Default (0, 1) = all tiles.  Replaces BlockGenerator::next
+ * as the work scheduler (ref: src/block.cpp:119-152). */
+int nb_set_tiles(nb_ctx *, int rank, int nranks);
+
+/* Replaces the body of render() (ref: src/main.cpp:61-119): BlockGenerator + TBB loop + renderBlock +
+ * ImageBlock::put x2.  Writes the (H+2b) x (W+2b) x 4 fp32 row-major UN-normalised weighted film including
+ * the border -- byte compatible with ImageBlock storage (ref: include/nori/block.h:35, src/block.cpp:36) so that
+ * toBitmap / EXR / GUI code is unchanged.  film_host is caller-owned HOST memory. */
+int nb_render(nb_ctx *, float *film_host, nb_stats *stats);
+
+/* Same, but the film stays on the device (film_dev: device pointer on the context's device) and all work is
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the context's own stream).  Used by the
+ * multi-GPU driver, which exchanges films with NCCL. */
+int nb_render_device(nb_ctx *, float *film_dev, void *stream, nb_stats *stats);
+
+/* Finished ImageBlocks of this context's tiles, packed: blocks_dev receives ntiles_mine x (32+2b) x (32+2b) x 4 fp32
+ * (tile order = ascending tile_id of the tiles owned by (rank, nranks)); the frame-end exchange gathers these. */
+int nb_render_blocks_device(nb_ctx *, float *blocks_dev, void *stream, nb_stats *stats);
+/* Number of tiles owned by (rank, nranks) for the current camera, and the block edge (32 + 2*border). */
+int nb_tile_count(nb_ctx *, int rank, int nranks, int *ntiles, int *block_edge);
+/* Adds packed blocks of (rank, nranks) into a full film on the device: the merge of ImageBlock::put(ImageBlock&)
+ * (ref: src/block.cpp:93-102).  film_dev must be zeroed by the caller before the first merge. */
+int nb_merge_blocks_device(nb_ctx *, const float *blocks_dev, int rank, int nranks, float *film_dev, void *stream);
+
+/* Batched Scene::rayIntersect (ref: include/nori/scene.h:63-65,82-85 -> src/accel.cpp:23-43).  HOST buffers.
+ * shadow != 0: any-hit query, hits[i].prim = 0 if occluded else NB_MISS. */
+int nb_intersect(nb_ctx *, const nb_ray *rays, uint64_t n, nb_hit *hits, int shadow, nb_stats *stats);
+/* Device-buffer variant (rays_dev / hits_dev on the context's device). */
+int nb_intersect_device(nb_ctx *, const nb_ray *rays_dev, uint64_t n, nb_hit *hits_dev, int shadow, void *stream, nb_stats *stats);
+/* Full intersection records (ref: src/accel.cpp:45-96): out16[i] = p(3) t uv(2) shFrame.s(3) .t(3) .n(3) mesh. */
+int nb_intersect_full(nb_ctx *, const nb_ray *rays, uint64_t n, float *out16);
+
+/* Film normalisation: ImageBlock::toBitmap (ref: src/block.cpp:45-51, include/nori/color.h:100-105). HOST buffers. */
+int nb_film_to_rgb(nb_ctx *, const float *film_host, float *rgb_host);
+
+/* Tuning knobs (optional; sane defaults): key/value, see DESIGN.md section 6.  Unknown key -> error. */
+int nb_set_option(nb_ctx *, const char *key, int64_t value);
+/* Scene geometry summary after nb_build_accel. */
+int nb_scene_info(nb_ctx *, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_bytes, int *bvh_depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
