@@ -1,0 +1,232 @@
+"""ctypes binding of the C-ABI in include/nori_b200.h (libnori_b200.so).
+
+The library is the product: there is no Python or CPU fallback behind these calls.  If the shared
+object is missing or no CUDA device is usable the functions raise -- loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnori_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nori_b200.h")
+
+
+class NoriError(RuntimeError):
+    """Mirror of NoriException (ref: include/nori/common.h:135-140) for errors crossing the C-ABI."""
+
+
+class BsdfDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("albedo", C.c_float * 3), ("alpha", C.c_float),
+                ("intIOR", C.c_float), ("extIOR", C.c_float), ("ks", C.c_float)]
+
+
+class EmitterDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("radiance", C.c_float * 3)]
+
+
+class IntegratorDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("rr_start", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("hits_shaded", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+                ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("mint", np.float32), ("d", np.float32, 3), ("maxt", np.float32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("prim", np.uint32), ("mesh", np.uint32)])
+
+_lib = None
+
+
+def declared_symbols():
+    """Every entry point include/nori_b200.h declares."""
+    src = open(HEADER_PATH).read()
+    return sorted(set(re.findall(r"\b(nb_[a-z_0-9]+)\s*\(", src)) - {"nb_ctx"})
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NoriError(f"{LIB_PATH} is missing: run `python -m nori_b200.build` (there is no fallback path)")
+        L = C.CDLL(LIB_PATH)
+        vp, i, u32, u64, f = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_float
+        sp = C.POINTER(Stats)
+        L.nb_create.argtypes = [i]; L.nb_create.restype = vp
+        L.nb_destroy.argtypes = [vp]; L.nb_destroy.restype = None
+        L.nb_last_error.restype = C.c_char_p
+        L.nb_abi_version.restype = i
+        L.nb_add_mesh.argtypes = [vp, vp, u32, vp, vp, vp, u32, C.POINTER(BsdfDesc), C.POINTER(EmitterDesc)]
+        L.nb_clear_meshes.argtypes = [vp]
+        L.nb_build_accel.argtypes = [vp]
+        L.nb_upload_scene.argtypes = [vp]
+        L.nb_set_camera.argtypes = [vp, vp, vp, i, i, f, f]
+        L.nb_set_filter.argtypes = [vp, vp, f]
+        L.nb_set_sampler.argtypes = [vp, u32, i, u64]
+        L.nb_set_integrator.argtypes = [vp, C.POINTER(IntegratorDesc)]
+        L.nb_set_tiles.argtypes = [vp, i, i]
+        L.nb_render.argtypes = [vp, vp, sp]
+        L.nb_render_device.argtypes = [vp, vp, vp, sp]
+        L.nb_render_blocks_device.argtypes = [vp, vp, vp, sp]
+        L.nb_tile_count.argtypes = [vp, i, i, C.POINTER(i), C.POINTER(i)]
+        L.nb_merge_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
+        L.nb_intersect.argtypes = [vp, vp, u64, vp, i, sp]
+        L.nb_intersect_device.argtypes = [vp, vp, u64, vp, i, vp, sp]
+        L.nb_intersect_full.argtypes = [vp, vp, u64, vp]
+        L.nb_film_to_rgb.argtypes = [vp, vp, vp]
+        L.nb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.nb_scene_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i)]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc):
+    if rc != 0:
+        raise NoriError(lib().nb_last_error().decode())
+
+
+class Context:
+    """One GPU's render context (nb_ctx).  Mirrors the role of Scene's Accel + render() in the reference."""
+
+    def __init__(self, device: int = -1):
+        L = lib()
+        self.h = L.nb_create(device)
+        if not self.h:
+            raise NoriError(L.nb_last_error().decode())
+        self.scene = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().nb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- scene assembly (Scene::addChild / activate, ref: src/scene.cpp:27-79)
+    def set_option(self, key: str, value: int):
+        _check(lib().nb_set_option(self.h, key.encode(), int(value)))
+
+    def load(self, scene, build=True):
+        L = lib()
+        _check(L.nb_clear_meshes(self.h))
+        for m in scene.meshes:
+            b = BsdfDesc()
+            b.type = int(m.bsdf.type)
+            for k in range(3):
+                b.albedo[k] = float(m.bsdf.albedo[k])
+            b.alpha, b.intIOR, b.extIOR, b.ks = float(m.bsdf.alpha), float(m.bsdf.intIOR), float(m.bsdf.extIOR), float(m.bsdf.ks)
+            e = EmitterDesc()
+            if m.radiance is not None:
+                e.type = 1
+                for k in range(3):
+                    e.radiance[k] = float(m.radiance[k])
+            if L.nb_add_mesh(self.h, _p(m.V), m.V.shape[0], _p(m.N), _p(m.UV), _p(m.F), m.F.shape[0], C.byref(b), C.byref(e)) < 0:
+                raise NoriError(L.nb_last_error().decode())
+        if build:
+            _check(L.nb_build_accel(self.h))
+        self.configure(scene)
+
+    def configure(self, scene):
+        """Camera / filter / sampler / integrator state (cheap; no geometry work)."""
+        L = lib()
+        self.scene = scene
+        cam = scene.camera
+        s2c = np.ascontiguousarray(cam.s2c, dtype=np.float32)
+        c2w = np.ascontiguousarray(cam.c2w, dtype=np.float32)
+        _check(L.nb_set_camera(self.h, _p(s2c), _p(c2w), cam.width, cam.height, cam.nearClip, cam.farClip))
+        tab = np.ascontiguousarray(scene.filter_table, dtype=np.float32)
+        _check(L.nb_set_filter(self.h, _p(tab), scene.filter_radius))
+        _check(L.nb_set_sampler(self.h, scene.spp, scene.seed_mode, scene.seed))
+        it = IntegratorDesc(int(scene.integrator), int(scene.rr_start), int(scene.max_depth), 0)
+        _check(L.nb_set_integrator(self.h, C.byref(it)))
+
+    def upload(self):
+        _check(lib().nb_upload_scene(self.h))
+
+    def set_tiles(self, rank, nranks):
+        _check(lib().nb_set_tiles(self.h, rank, nranks))
+
+    def tile_count(self, rank, nranks):
+        n, e = C.c_int(), C.c_int()
+        _check(lib().nb_tile_count(self.h, rank, nranks, C.byref(n), C.byref(e)))
+        return n.value, e.value
+
+    def scene_info(self):
+        a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        _check(lib().nb_scene_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(tris=a.value, nodes=b.value, bytes=c.value, depth=d.value)
+
+    # ---- the path
+    def render(self, film: np.ndarray | None = None):
+        """nb_render: host film out (H+2b, W+2b, 4) -- the reference-facing call."""
+        if film is None:
+            film = np.zeros(self.scene.film_shape, dtype=np.float32)
+        st = Stats()
+        _check(lib().nb_render(self.h, _p(film), C.byref(st)))
+        return film, st
+
+    def render_host_ptr(self, host_ptr: int):
+        st = Stats()
+        _check(lib().nb_render(self.h, C.c_void_p(host_ptr), C.byref(st)))
+        return st
+
+    def render_device(self, film_ptr: int, stream: int = 0):
+        st = Stats()
+        _check(lib().nb_render_device(self.h, C.c_void_p(film_ptr), C.c_void_p(stream), C.byref(st)))
+        return st
+
+    def render_blocks_device(self, blocks_ptr: int, stream: int = 0):
+        st = Stats()
+        _check(lib().nb_render_blocks_device(self.h, C.c_void_p(blocks_ptr), C.c_void_p(stream), C.byref(st)))
+        return st
+
+    def merge_blocks_device(self, blocks_ptr: int, rank: int, nranks: int, film_ptr: int, stream: int = 0):
+        _check(lib().nb_merge_blocks_device(self.h, C.c_void_p(blocks_ptr), rank, nranks, C.c_void_p(film_ptr), C.c_void_p(stream)))
+
+    def intersect(self, rays: np.ndarray, shadow=False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        st = Stats()
+        _check(lib().nb_intersect(self.h, _p(rays), rays.shape[0], _p(hits), int(shadow), C.byref(st)))
+        return hits, st
+
+    def intersect_device(self, rays_ptr: int, n: int, hits_ptr: int, shadow=False, stream: int = 0):
+        st = Stats()
+        _check(lib().nb_intersect_device(self.h, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr), int(shadow), C.c_void_p(stream), C.byref(st)))
+        return st
+
+    def intersect_full(self, rays: np.ndarray):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        out = np.zeros((rays.shape[0], 16), dtype=np.float32)
+        _check(lib().nb_intersect_full(self.h, _p(rays), rays.shape[0], _p(out)))
+        return out
+
+    def film_to_rgb(self, film: np.ndarray):
+        film = np.ascontiguousarray(film, dtype=np.float32)
+        rgb = np.zeros((self.scene.camera.height, self.scene.camera.width, 3), dtype=np.float32)
+        _check(lib().nb_film_to_rgb(self.h, _p(film), _p(rgb)))
+        return rgb

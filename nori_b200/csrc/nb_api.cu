@@ -1,0 +1,583 @@
+// nb_api.cu -- C-ABI of libnori_b200.so (see include/nori_b200.h for the contract and reference citations).
+//
+// No CPU fallback exists in this file: every entry point either runs the sm_100a kernels or fails with an
+// error.  The oracle (oracle/) is never linked or called from here.
+#include "../../include/nori_b200.h"
+#include "nb_bvh.h"
+#include "nb_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct HostMesh {
+    std::vector<float> V, N, UV;
+    std::vector<uint32_t> F;
+    uint32_t nv = 0, nf = 0;
+    nb_bsdf_desc bsdf;
+    nb_emitter_desc emitter;
+};
+
+template <typename T>
+struct DevBuf {
+    T *d = nullptr; T *h = nullptr; size_t n = 0;   // device + pinned host mirror
+    void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = nullptr; h = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        release(); n = count;
+        size_t bytes = sizeof(T) * (count ? count : 1);
+        cudaError_t e = cudaMalloc(&d, bytes); if (e != cudaSuccess) return e;
+        return cudaMallocHost(&h, bytes);
+    }
+    size_t bytes() const { return sizeof(T) * n; }
+};
+
+}  // namespace
+
+struct nb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    int sm_count = 0;
+    std::vector<HostMesh> meshes;
+    // scene tables (device + pinned mirrors)
+    DevBuf<float4> nodes, tris, verts, normals;
+    DevBuf<float2> uvs;
+    DevBuf<uint4> faces;
+    DevBuf<nb::DevMesh> dmeshes;
+    DevBuf<float> cdf;
+    DevBuf<int32_t> emitters;
+    uint32_t n_nodes = 0, n_prims = 0, top_nodes = 0; int bvh_depth = 0; bool built = false;
+    double build_seconds = 0;
+    // camera / film / sampler / integrator
+    float s2c[16], c2w[16]; int W = 0, H = 0; float nearClip = 1e-4f, farClip = 1e4f; bool have_camera = false;
+    float ftable[33]; float fradius = 2.0f; int border = 2;
+    uint32_t spp = 1; int seed_mode = NB_SEED_PER_SAMPLE; uint64_t seed = 0;
+    nb_integrator_desc integ = { NB_INT_NORMALS, 3, 0, 0 };
+    int tile_rank = 0, tile_nranks = 1;
+    // work buffers
+    float4 *blocks = nullptr; size_t blocks_cap = 0;
+    float4 *film = nullptr; size_t film_cap = 0;
+    unsigned long long *counters = nullptr;          // 8 x u64 device
+    unsigned long long *counters_h = nullptr;        // pinned
+    // options
+    int64_t opt_blocks_per_sm = 0, opt_refill = 8, opt_smem_nodes = 0, opt_chunk = 16, opt_count = 0, opt_max_leaf = 4,
+            opt_bfs_nodes = 2048;
+};
+
+namespace {
+
+int tiles_for(const nb_ctx *c, int rank, int nranks, int *ntx_out, int *nty_out) {
+    int ntx = (c->W + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE, nty = (c->H + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE;
+    if (ntx_out) *ntx_out = ntx;
+    if (nty_out) *nty_out = nty;
+    int total = ntx * nty;
+    return total > rank ? (total - rank + nranks - 1) / nranks : 0;
+}
+
+int ensure_device(nb_ctx *c) { CK(cudaSetDevice(c->device)); return 0; }
+
+int fill_scene(nb_ctx *c, nb::SceneDev &sc) {
+    if (!c->built) return fail("nb_build_accel has not been called");
+    sc.nodes = c->nodes.d; sc.tris = c->tris.d; sc.faces = c->faces.d; sc.verts = c->verts.d; sc.normals = c->normals.d;
+    sc.uvs = c->uvs.d; sc.meshes = c->dmeshes.d; sc.emitter_cdf = c->cdf.d; sc.emitters = c->emitters.d;
+    sc.n_emitters = (int32_t) c->emitters.n; sc.n_nodes = c->n_nodes; sc.n_prims = c->n_prims;
+    return 0;
+}
+
+template <int INTEG>
+void launch_render(const nb::RenderParams &P, bool count, bool block_mode, int grid, size_t smem, cudaStream_t s) {
+    if (block_mode) {
+        int g = (P.n_my_tiles + 31) / 32;
+        if (count) nb::render_block_mode_kernel<INTEG, true><<<g, 32, 0, s>>>(P);
+        else nb::render_block_mode_kernel<INTEG, false><<<g, 32, 0, s>>>(P);
+    } else {
+        if (count) nb::render_kernel<INTEG, true><<<grid, 128, smem, s>>>(P);
+        else nb::render_kernel<INTEG, false><<<grid, 128, smem, s>>>(P);
+    }
+}
+
+template <int INTEG>
+cudaError_t occupancy(int *blocks, bool count, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = count ? cudaFuncSetAttribute(nb::render_kernel<INTEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)
+                              : cudaFuncSetAttribute(nb::render_kernel<INTEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+    }
+    return count ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, nb::render_kernel<INTEG, true>, 128, smem)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, nb::render_kernel<INTEG, false>, 128, smem);
+}
+
+// Renders this context's tiles into c->blocks (or blocks_out) on stream s.
+int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, int *n_tiles_out) {
+    if (ensure_device(c)) return 1;
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    nb::RenderParams P;
+    memset(&P, 0, sizeof P);
+    if (fill_scene(c, P.sc)) return 1;
+    if (c->integ.type < NB_INT_NORMALS || c->integ.type > NB_INT_PATH_MIS) return fail("unsupported integrator type %d (no CPU fallback)", c->integ.type);
+    memcpy(P.s2c, c->s2c, sizeof P.s2c); memcpy(P.c2w, c->c2w, sizeof P.c2w);
+    P.W = c->W; P.H = c->H; P.invW = 1.0f / (float) c->W; P.invH = 1.0f / (float) c->H;   // cwiseInverse, ref: src/perspective.cpp:27
+    P.nearClip = c->nearClip; P.farClip = c->farClip;
+    memcpy(P.ftable, c->ftable, sizeof P.ftable);
+    P.fradius = c->fradius; P.lookup = NB_FILTER_RESOLUTION / c->fradius; P.border = c->border;   // ref: src/block.cpp:20,27
+    P.spp = c->spp; P.seed_mode = c->seed_mode; P.seed = c->seed;
+    P.integrator = c->integ.type; P.rr_start = c->integ.rr_start > 0 ? c->integ.rr_start : 3;
+    P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
+    P.tile_rank = c->tile_rank; P.tile_nranks = c->tile_nranks;
+    P.n_my_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, &P.ntx, &P.nty);
+    P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
+    if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
+    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(c->opt_chunk, c->spp));
+    P.nchunks = (c->spp + P.chunk - 1) / P.chunk;
+    const unsigned long long units = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
+    if (units > 0xffffffffULL) return fail("too many work units");
+    P.n_units = (uint32_t) units;
+    const size_t blk_elems = (size_t) P.n_my_tiles * P.block_edge * P.block_edge;
+    if (!blocks_out) {
+        if (blk_elems > c->blocks_cap) {
+            if (c->blocks) cudaFree(c->blocks);
+            c->blocks = nullptr; c->blocks_cap = 0;
+            CK(cudaMalloc(&c->blocks, sizeof(float4) * (blk_elems ? blk_elems : 1)));
+            c->blocks_cap = blk_elems;
+        }
+        blocks_out = c->blocks;
+    }
+    P.blocks = blocks_out;
+    P.counters = c->counters;
+    P.refill_threshold = (int) std::max<int64_t>(1, std::min<int64_t>(32, c->opt_refill));
+    const bool block_mode = c->seed_mode == NB_SEED_PER_BLOCK;
+    P.smem_nodes = block_mode ? 0 : (int) std::min<int64_t>(std::min<int64_t>(c->opt_smem_nodes, c->top_nodes), 3400);
+    const size_t smem = (size_t) P.smem_nodes * 64;
+    const bool count = c->opt_count != 0;
+
+    int occ = 0;
+    cudaError_t oe = cudaSuccess;
+    switch (c->integ.type) {
+        case 0: oe = occupancy<0>(&occ, count, smem); break; case 1: oe = occupancy<1>(&occ, count, smem); break;
+        case 2: oe = occupancy<2>(&occ, count, smem); break; case 3: oe = occupancy<3>(&occ, count, smem); break;
+        case 4: oe = occupancy<4>(&occ, count, smem); break; default: oe = occupancy<5>(&occ, count, smem); break;
+    }
+    if (oe != cudaSuccess) return fail("occupancy query failed: %s", cudaGetErrorString(oe));
+    if (occ < 1) return fail("render kernel does not fit on an SM (smem %zu B)", smem);
+    if (c->opt_blocks_per_sm > 0) occ = (int) std::min<int64_t>(occ, c->opt_blocks_per_sm);
+    const int grid = c->sm_count * occ;    // persistent: a whole number of CTAs per SM
+
+    CK(cudaEventRecord(c->ev[0], s));
+    CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s));
+    if (blk_elems) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));
+    CK(cudaEventRecord(c->ev[1], s));
+    if (P.n_my_tiles > 0) {
+        switch (c->integ.type) {
+            case 0: launch_render<0>(P, count, block_mode, grid, smem, s); break;
+            case 1: launch_render<1>(P, count, block_mode, grid, smem, s); break;
+            case 2: launch_render<2>(P, count, block_mode, grid, smem, s); break;
+            case 3: launch_render<3>(P, count, block_mode, grid, smem, s); break;
+            case 4: launch_render<4>(P, count, block_mode, grid, smem, s); break;
+            default: launch_render<5>(P, count, block_mode, grid, smem, s); break;
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev[2], s));
+    if (n_tiles_out) *n_tiles_out = P.n_my_tiles;
+    if (st) {
+        memset(st, 0, sizeof *st);
+        // samples rendered by this context
+        unsigned long long ns = 0;
+        for (int k = 0; k < P.n_my_tiles; ++k) {
+            int tile_id = c->tile_rank + k * c->tile_nranks, bx = tile_id % P.ntx, by = tile_id / P.ntx;
+            ns += (unsigned long long) std::min(32, c->W - bx * 32) * std::min(32, c->H - by * 32);
+        }
+        st->samples = ns * c->spp;
+        st->launches = P.n_my_tiles > 0 ? 1 : 0;
+    }
+    return 0;
+}
+
+int merge(nb_ctx *c, const float4 *blocks, int n_tiles, int rank, int nranks, float4 *film, cudaStream_t s) {
+    if (n_tiles <= 0) return 0;
+    int ntx = (c->W + 31) / 32;
+    int edge = NB_BLOCK_SIZE + 2 * c->border;
+    long long total = (long long) n_tiles * edge * edge;
+    int grid = (int) ((total + 255) / 256);
+    nb::merge_blocks_kernel<<<grid, 256, 0, s>>>(blocks, n_tiles, rank, nranks, ntx, c->W, c->H, c->border, edge, film);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int finish_stats(nb_ctx *c, cudaStream_t s, nb_stats *st, int extra_launches) {
+    CK(cudaMemcpyAsync(c->counters_h, c->counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(c->ev[3], s));
+    CK(cudaStreamSynchronize(s));
+    if (st) {
+        st->rays = c->counters_h[1]; st->node_visits = c->counters_h[2]; st->tri_tests = c->counters_h[3];
+        st->hits_shaded = c->counters_h[4];
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); st->kernel_ms = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[3])); st->total_ms = ms;
+        st->launches += extra_launches;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nb_last_error(void) { return g_err.c_str(); }
+int nb_abi_version(void) { return NB_ABI_VERSION; }
+
+nb_ctx *nb_create(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { fail("no CUDA device available (%s); libnori_b200 has no CPU fallback", cudaGetErrorString(e)); return nullptr; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) { fail("device %d out of range (%d devices)", device, ndev); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail("cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major < 10) { fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return nullptr; }
+    nb_ctx *c = new nb_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->counters, sizeof(unsigned long long) * 8) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->counters_h, sizeof(unsigned long long) * 8) == cudaSuccess;
+    if (!ok) { fail("context allocation failed: %s", cudaGetErrorString(cudaGetLastError())); nb_destroy(c); return nullptr; }
+    // default Gaussian filter (ref: src/perspective.cpp:71-73, src/rfilter.cpp:16-30)
+    for (int i = 0; i < NB_FILTER_RESOLUTION; ++i) {
+        float pos = (2.0f * i) / NB_FILTER_RESOLUTION, alpha = -1.0f / (2.0f * 0.5f * 0.5f);
+        c->ftable[i] = std::max(0.0f, std::exp(alpha * pos * pos) - std::exp(alpha * 2.0f * 2.0f));
+    }
+    c->ftable[NB_FILTER_RESOLUTION] = 0.0f;
+    return c;
+}
+
+void nb_destroy(nb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->nodes.release(); c->tris.release(); c->verts.release(); c->normals.release(); c->uvs.release(); c->faces.release();
+    c->dmeshes.release(); c->cdf.release(); c->emitters.release();
+    if (c->blocks) cudaFree(c->blocks);
+    if (c->film) cudaFree(c->film);
+    if (c->counters) cudaFree(c->counters);
+    if (c->counters_h) cudaFreeHost(c->counters_h);
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int nb_add_mesh(nb_ctx *c, const float *V, uint32_t nv, const float *N, const float *UV, const uint32_t *F, uint32_t nf,
+                const nb_bsdf_desc *bsdf, const nb_emitter_desc *emitter) {
+    if (!c) { fail("null context"); return -1; }
+    if ((!V && nv) || (!F && nf)) { fail("nb_add_mesh: null vertex/index array"); return -1; }
+    for (size_t i = 0; i < (size_t) nf * 3; ++i) if (F[i] >= nv) { fail("nb_add_mesh: index %u out of range (nv=%u)", F[i], nv); return -1; }
+    HostMesh m;
+    m.nv = nv; m.nf = nf;
+    m.V.assign(V, V + (size_t) nv * 3);
+    if (N) m.N.assign(N, N + (size_t) nv * 3);
+    if (UV) m.UV.assign(UV, UV + (size_t) nv * 2);
+    m.F.assign(F, F + (size_t) nf * 3);
+    if (bsdf) {
+        if (bsdf->type < NB_BSDF_DIFFUSE || bsdf->type > NB_BSDF_MICROFACET) { fail("unsupported BSDF type %d (no CPU fallback)", bsdf->type); return -1; }
+        m.bsdf = *bsdf;
+    } else {   // default diffuse, ref: src/mesh.cpp:23-29, src/diffuse.cpp:19
+        memset(&m.bsdf, 0, sizeof m.bsdf); m.bsdf.type = NB_BSDF_DIFFUSE; m.bsdf.albedo[0] = m.bsdf.albedo[1] = m.bsdf.albedo[2] = 0.5f;
+    }
+    if (emitter) {
+        if (emitter->type != NB_EMITTER_NONE && emitter->type != NB_EMITTER_AREA) { fail("unsupported emitter type %d", emitter->type); return -1; }
+        m.emitter = *emitter;
+    } else memset(&m.emitter, 0, sizeof m.emitter);
+    c->meshes.push_back(std::move(m));
+    c->built = false;
+    return (int) c->meshes.size() - 1;
+}
+
+int nb_clear_meshes(nb_ctx *c) { if (!c) return fail("null context"); c->meshes.clear(); c->built = false; return 0; }
+
+int nb_upload_scene(nb_ctx *c) {
+    if (!c) return fail("null context");
+    if (!c->built) return fail("nb_build_accel has not been called");
+    if (ensure_device(c)) return 1;
+    cudaStream_t s = c->stream;
+#define UP(buf) CK(cudaMemcpyAsync(buf.d, buf.h, buf.bytes(), cudaMemcpyHostToDevice, s))
+    UP(c->nodes); UP(c->tris); UP(c->verts); UP(c->normals); UP(c->uvs); UP(c->faces); UP(c->dmeshes); UP(c->cdf); UP(c->emitters);
+#undef UP
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int nb_build_accel(nb_ctx *c) {
+    if (!c) return fail("null context");
+    if (ensure_device(c)) return 1;
+    size_t nv = 0, nf = 0, ncdf = 0, nem = 0;
+    for (auto &m : c->meshes) { nv += m.nv; nf += m.nf; if (m.emitter.type == NB_EMITTER_AREA) { ncdf += m.nf + 1; nem++; } }
+    if (nf >= (1u << 28)) return fail("too many triangles (%zu)", nf);
+    CK(c->verts.alloc(nv)); CK(c->normals.alloc(nv)); CK(c->uvs.alloc(nv)); CK(c->faces.alloc(nf));
+    CK(c->dmeshes.alloc(c->meshes.size())); CK(c->cdf.alloc(ncdf)); CK(c->emitters.alloc(nem));
+    size_t vo = 0, fo = 0, co = 0, eo = 0;
+    for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
+        const HostMesh &m = c->meshes[mi];
+        for (uint32_t i = 0; i < m.nv; ++i) {
+            c->verts.h[vo + i] = make_float4(m.V[3 * i], m.V[3 * i + 1], m.V[3 * i + 2], 0.f);
+            c->normals.h[vo + i] = m.N.empty() ? make_float4(0, 0, 0, 0) : make_float4(m.N[3 * i], m.N[3 * i + 1], m.N[3 * i + 2], 0.f);
+            c->uvs.h[vo + i] = m.UV.empty() ? make_float2(0, 0) : make_float2(m.UV[2 * i], m.UV[2 * i + 1]);
+        }
+        for (uint32_t f = 0; f < m.nf; ++f)
+            c->faces.h[fo + f] = make_uint4((uint32_t) vo + m.F[3 * f], (uint32_t) vo + m.F[3 * f + 1], (uint32_t) vo + m.F[3 * f + 2], (uint32_t) mi);
+        nb::DevMesh &d = c->dmeshes.h[mi];
+        memset(&d, 0, sizeof d);
+        d.bsdf_type = m.bsdf.type; memcpy(d.albedo, m.bsdf.albedo, sizeof d.albedo);
+        d.alpha = m.bsdf.alpha; d.intIOR = m.bsdf.intIOR; d.extIOR = m.bsdf.extIOR; d.ks = m.bsdf.ks;
+        d.emitter_type = m.emitter.type; memcpy(d.radiance, m.emitter.radiance, sizeof d.radiance);
+        d.prim_offset = (uint32_t) fo; d.nf = m.nf;
+        d.flags = (m.N.empty() ? 0u : 1u) | (m.UV.empty() ? 0u : 2u);
+        if (m.emitter.type == NB_EMITTER_AREA) {
+            // DiscretePDF over triangle areas: ref src/mesh.cpp:31-37, include/nori/dpdf.h:40-84
+            float *cdf = c->cdf.h + co;
+            cdf[0] = 0.0f;
+            for (uint32_t f = 0; f < m.nf; ++f) {
+                const float *p0 = &m.V[3 * m.F[3 * f]], *p1 = &m.V[3 * m.F[3 * f + 1]], *p2 = &m.V[3 * m.F[3 * f + 2]];
+                float e1[3] = { p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2] }, e2[3] = { p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2] };
+                float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+                float area = 0.5f * std::sqrt(cx * cx + (cy * cy + cz * cz));
+                cdf[f + 1] = cdf[f] + area;
+            }
+            d.area_sum = cdf[m.nf];
+            if (d.area_sum > 0) {
+                float norm = 1.0f / d.area_sum;
+                for (uint32_t f = 1; f <= m.nf; ++f) cdf[f] *= norm;
+                cdf[m.nf] = 1.0f;
+            }
+            d.cdf_offset = (uint32_t) co;
+            c->emitters.h[eo++] = (int32_t) mi;
+            co += m.nf + 1;
+        }
+        vo += m.nv; fo += m.nf;
+    }
+    nb::BvhInput in; in.verts = reinterpret_cast<const float *>(c->verts.h); in.faces = reinterpret_cast<const uint32_t *>(c->faces.h);
+    in.nprims = (uint32_t) nf;
+    nb::BvhOutput out;
+    nb::build_bvh(in, out, (int) c->opt_max_leaf, (uint32_t) c->opt_bfs_nodes, 0);
+    c->n_nodes = out.nnodes; c->n_prims = (uint32_t) nf; c->top_nodes = out.top_nodes; c->bvh_depth = out.depth;
+    c->build_seconds = out.build_seconds;
+    if (out.depth >= nb::kStack) return fail("BVH too deep (%d)", out.depth);
+    CK(c->nodes.alloc((size_t) out.nnodes * 4)); CK(c->tris.alloc(out.tris.size() / 4));
+    memcpy(c->nodes.h, out.nodes.data(), out.nodes.size() * sizeof(float));
+    if (!out.tris.empty()) memcpy(c->tris.h, out.tris.data(), out.tris.size() * sizeof(float));
+    c->built = true;
+    return nb_upload_scene(c);
+}
+
+int nb_set_camera(nb_ctx *c, const float s2c[16], const float c2w[16], int width, int height, float nearClip, float farClip) {
+    if (!c) return fail("null context");
+    if (width <= 0 || height <= 0 || width > 32767 || height > 32767) return fail("invalid output size %dx%d", width, height);
+    memcpy(c->s2c, s2c, sizeof c->s2c); memcpy(c->c2w, c2w, sizeof c->c2w);
+    c->W = width; c->H = height; c->nearClip = nearClip; c->farClip = farClip; c->have_camera = true;
+    return 0;
+}
+
+int nb_set_filter(nb_ctx *c, const float table[NB_FILTER_RESOLUTION + 1], float radius) {
+    if (!c) return fail("null context");
+    if (!(radius > 0)) return fail("invalid filter radius %f", radius);
+    int border = (int) std::ceil(radius - 0.5f);     // ref: src/block.cpp:20
+    if (border > 8) return fail("filter radius %f too large", radius);
+    memcpy(c->ftable, table, sizeof c->ftable);
+    c->fradius = radius; c->border = border;
+    return 0;
+}
+
+int nb_set_sampler(nb_ctx *c, uint32_t spp, int seed_mode, uint64_t seed) {
+    if (!c) return fail("null context");
+    if (spp == 0) return fail("sampleCount must be >= 1");
+    if (seed_mode != NB_SEED_PER_SAMPLE && seed_mode != NB_SEED_PER_BLOCK) return fail("unknown seed mode %d", seed_mode);
+    c->spp = spp; c->seed_mode = seed_mode; c->seed = seed;
+    return 0;
+}
+
+int nb_set_integrator(nb_ctx *c, const nb_integrator_desc *d) {
+    if (!c || !d) return fail("null argument");
+    if (d->type < NB_INT_NORMALS || d->type > NB_INT_PATH_MIS) return fail("unsupported integrator type %d (no CPU fallback)", d->type);
+    c->integ = *d;
+    return 0;
+}
+
+int nb_set_tiles(nb_ctx *c, int rank, int nranks) {
+    if (!c) return fail("null context");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("invalid tile shard (%d of %d)", rank, nranks);
+    c->tile_rank = rank; c->tile_nranks = nranks;
+    return 0;
+}
+
+int nb_tile_count(nb_ctx *c, int rank, int nranks, int *ntiles, int *block_edge) {
+    if (!c) return fail("null context");
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("invalid tile shard (%d of %d)", rank, nranks);
+    if (ntiles) *ntiles = tiles_for(c, rank, nranks, nullptr, nullptr);
+    if (block_edge) *block_edge = NB_BLOCK_SIZE + 2 * c->border;
+    return 0;
+}
+
+int nb_render_blocks_device(nb_ctx *c, float *blocks_dev, void *stream, nb_stats *st) {
+    if (!c || !blocks_dev) return fail("null argument");
+    cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
+    if (render_blocks(c, reinterpret_cast<float4 *>(blocks_dev), s, st, nullptr)) return 1;
+    return finish_stats(c, s, st, 0);
+}
+
+int nb_merge_blocks_device(nb_ctx *c, const float *blocks_dev, int rank, int nranks, float *film_dev, void *stream) {
+    if (!c || !blocks_dev || !film_dev) return fail("null argument");
+    if (ensure_device(c)) return 1;
+    cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
+    int n = tiles_for(c, rank, nranks, nullptr, nullptr);
+    return merge(c, reinterpret_cast<const float4 *>(blocks_dev), n, rank, nranks, reinterpret_cast<float4 *>(film_dev), s);
+}
+
+int nb_render_device(nb_ctx *c, float *film_dev, void *stream, nb_stats *st) {
+    if (!c || !film_dev) return fail("null argument");
+    cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
+    int n_tiles = 0;
+    if (render_blocks(c, nullptr, s, st, &n_tiles)) return 1;
+    const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
+    CK(cudaMemsetAsync(film_dev, 0, sizeof(float4) * film_elems, s));
+    if (merge(c, c->blocks, n_tiles, c->tile_rank, c->tile_nranks, reinterpret_cast<float4 *>(film_dev), s)) return 1;
+    return finish_stats(c, s, st, n_tiles > 0 ? 1 : 0);
+}
+
+int nb_render(nb_ctx *c, float *film_host, nb_stats *st) {
+    if (!c || !film_host) return fail("null argument");
+    if (ensure_device(c)) return 1;
+    const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
+    if (film_elems > c->film_cap) {
+        if (c->film) cudaFree(c->film);
+        c->film = nullptr; c->film_cap = 0;
+        CK(cudaMalloc(&c->film, sizeof(float4) * (film_elems ? film_elems : 1)));
+        c->film_cap = film_elems;
+    }
+    cudaStream_t s = c->stream;
+    int n_tiles = 0;
+    if (render_blocks(c, nullptr, s, st, &n_tiles)) return 1;
+    CK(cudaMemsetAsync(c->film, 0, sizeof(float4) * film_elems, s));
+    if (merge(c, c->blocks, n_tiles, c->tile_rank, c->tile_nranks, c->film, s)) return 1;
+    CK(cudaMemcpyAsync(film_host, c->film, sizeof(float4) * film_elems, cudaMemcpyDeviceToHost, s));
+    if (finish_stats(c, s, st, n_tiles > 0 ? 1 : 0)) return 1;
+    if (st) { st->d2h_bytes = sizeof(float4) * film_elems; st->h2d_bytes = sizeof(nb::RenderParams); }
+    return 0;
+}
+
+int nb_intersect_device(nb_ctx *c, const nb_ray *rays_dev, uint64_t n, nb_hit *hits_dev, int shadow, void *stream, nb_stats *st) {
+    if (!c) return fail("null context");
+    if (ensure_device(c)) return 1;
+    nb::SceneDev sc;
+    if (fill_scene(c, sc)) return 1;
+    cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
+    CK(cudaEventRecord(c->ev[0], s));
+    CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s));
+    CK(cudaEventRecord(c->ev[1], s));
+    if (n) {
+        int grid = (int) std::min<uint64_t>((n + 127) / 128, (uint64_t) c->sm_count * 16);
+        if (c->opt_count) nb::intersect_kernel<true><<<grid, 128, 0, s>>>(sc, reinterpret_cast<const float4 *>(rays_dev), n, reinterpret_cast<nb::HitOut *>(hits_dev), shadow, nullptr, c->counters);
+        else nb::intersect_kernel<false><<<grid, 128, 0, s>>>(sc, reinterpret_cast<const float4 *>(rays_dev), n, reinterpret_cast<nb::HitOut *>(hits_dev), shadow, nullptr, c->counters);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev[2], s));
+    if (st) { memset(st, 0, sizeof *st); st->launches = n ? 1 : 0; }
+    return finish_stats(c, s, st, 0);
+}
+
+int nb_intersect(nb_ctx *c, const nb_ray *rays, uint64_t n, nb_hit *hits, int shadow, nb_stats *st) {
+    if (!c || (n && (!rays || !hits))) return fail("null argument");
+    if (ensure_device(c)) return 1;
+    if (n == 0) { if (st) memset(st, 0, sizeof *st); return 0; }
+    nb_ray *dr = nullptr; nb_hit *dh = nullptr;
+    CK(cudaMalloc(&dr, sizeof(nb_ray) * n));
+    if (cudaMalloc(&dh, sizeof(nb_hit) * n) != cudaSuccess) { cudaFree(dr); return fail("cudaMalloc failed"); }
+    int rc = 0;
+    if (cudaMemcpyAsync(dr, rays, sizeof(nb_ray) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = fail("H2D copy failed");
+    if (!rc) rc = nb_intersect_device(c, dr, n, dh, shadow, c->stream, st);
+    if (!rc && cudaMemcpy(hits, dh, sizeof(nb_hit) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
+    cudaFree(dr); cudaFree(dh);
+    if (!rc && st) { st->h2d_bytes = sizeof(nb_ray) * n; st->d2h_bytes = sizeof(nb_hit) * n; }
+    return rc;
+}
+
+int nb_intersect_full(nb_ctx *c, const nb_ray *rays, uint64_t n, float *out16) {
+    if (!c || (n && (!rays || !out16))) return fail("null argument");
+    if (ensure_device(c)) return 1;
+    if (n == 0) return 0;
+    nb::SceneDev sc;
+    if (fill_scene(c, sc)) return 1;
+    nb_ray *dr = nullptr; float *df = nullptr;
+    CK(cudaMalloc(&dr, sizeof(nb_ray) * n));
+    if (cudaMalloc(&df, sizeof(float) * 16 * n) != cudaSuccess) { cudaFree(dr); return fail("cudaMalloc failed"); }
+    int rc = 0;
+    if (cudaMemcpy(dr, rays, sizeof(nb_ray) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("H2D copy failed");
+    if (!rc) {
+        int grid = (int) std::min<uint64_t>((n + 127) / 128, (uint64_t) c->sm_count * 16);
+        nb::intersect_kernel<false><<<grid, 128, 0, c->stream>>>(sc, reinterpret_cast<const float4 *>(dr), n, nullptr, 0, df, nullptr);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("intersect kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc && cudaMemcpy(out16, df, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
+    cudaFree(dr); cudaFree(df);
+    return rc;
+}
+
+int nb_film_to_rgb(nb_ctx *c, const float *film_host, float *rgb_host) {
+    if (!c || !film_host || !rgb_host) return fail("null argument");
+    if (ensure_device(c)) return 1;
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
+    float4 *df = nullptr; float *dr = nullptr;
+    CK(cudaMalloc(&df, sizeof(float4) * film_elems));
+    if (cudaMalloc(&dr, sizeof(float) * 3 * c->W * c->H) != cudaSuccess) { cudaFree(df); return fail("cudaMalloc failed"); }
+    int rc = 0;
+    if (cudaMemcpy(df, film_host, sizeof(float4) * film_elems, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("H2D copy failed");
+    if (!rc) {
+        nb::film_to_rgb_kernel<<<(c->W * c->H + 255) / 256, 256, 0, c->stream>>>(df, c->W, c->H, c->border, dr);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("film_to_rgb kernel failed");
+    }
+    if (!rc && cudaMemcpy(rgb_host, dr, sizeof(float) * 3 * c->W * c->H, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
+    cudaFree(df); cudaFree(dr);
+    return rc;
+}
+
+int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
+    if (!c || !key) return fail("null argument");
+    std::string k(key);
+    if (k == "blocks_per_sm") c->opt_blocks_per_sm = value;
+    else if (k == "refill_threshold") c->opt_refill = value;
+    else if (k == "smem_nodes") c->opt_smem_nodes = value;
+    else if (k == "chunk") c->opt_chunk = value;
+    else if (k == "count") c->opt_count = value;
+    else if (k == "max_leaf") { c->opt_max_leaf = value; c->built = false; }
+    else if (k == "bfs_nodes") { c->opt_bfs_nodes = value; c->built = false; }
+    else return fail("unknown option \"%s\"", key);
+    return 0;
+}
+
+int nb_scene_info(nb_ctx *c, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_bytes, int *bvh_depth) {
+    if (!c) return fail("null context");
+    if (!c->built) return fail("nb_build_accel has not been called");
+    if (ntris) *ntris = c->n_prims;
+    if (nnodes) *nnodes = c->n_nodes;
+    if (scene_bytes) *scene_bytes = c->nodes.bytes() + c->tris.bytes() + c->verts.bytes() + c->normals.bytes() + c->uvs.bytes() + c->faces.bytes();
+    if (bvh_depth) *bvh_depth = c->bvh_depth;
+    return 0;
+}
+
+}  // extern "C"

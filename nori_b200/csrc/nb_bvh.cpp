@@ -1,0 +1,238 @@
+// nb_bvh.cpp -- binned-SAH BVH2 builder (host, multi-threaded).  See nb_bvh.h for the layout contract.
+//
+// The reference ships no hierarchy (brute force, ref: src/accel.cpp:30-43); results must not depend
+// on the tree, so every box is padded by a small multiple of the coordinate magnitude: the slab test may
+// then only cull candidates that Moeller-Trumbore (ref: src/mesh.cpp:39-76) would reject anyway.
+#include "nb_bvh.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+
+namespace nb {
+namespace {
+
+constexpr int kBins = 16;
+constexpr float kInf = std::numeric_limits<float>::infinity();
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = kInf; hi[a] = -kInf; } }
+    void grow(const Box &b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float *p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx < 0 ? 0.f : 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct PrimRef { Box b; float c[3]; };
+
+struct BNode {
+    Box box;
+    uint32_t left = 0, right = 0;   // valid if count == 0
+    uint32_t start = 0, count = 0;  // leaf if count > 0
+    int depth = 0;
+};
+
+struct Builder {
+    const PrimRef *prims;
+    uint32_t *order;
+    std::vector<BNode> nodes;
+    std::atomic<uint32_t> nnodes{0};
+    std::atomic<int> threads_free{0};
+    int max_leaf;
+
+    uint32_t alloc() { return nnodes.fetch_add(1); }
+
+    void build(uint32_t ni, uint32_t start, uint32_t end, int depth) {
+        Box box, cbox;
+        box.reset(); cbox.reset();
+        for (uint32_t i = start; i < end; ++i) { const PrimRef &p = prims[order[i]]; box.grow(p.b); cbox.grow(p.c); }
+        BNode &nd = nodes[ni];
+        nd.box = box; nd.depth = depth;
+        const uint32_t n = end - start;
+        if (n <= (uint32_t) max_leaf) { nd.start = start; nd.count = n; return; }
+
+        int best_axis = -1, best_bin = -1;
+        float best_cost = kInf;
+        if (depth < 44) {   // beyond that: balanced index splits, so the traversal stack (64) can never overflow
+            Box bins[3][kBins]; uint32_t cnt[3][kBins];
+            float scale[3];
+            for (int a = 0; a < 3; ++a) {
+                float ext = cbox.hi[a] - cbox.lo[a];
+                scale[a] = ext > 0 ? kBins / ext : 0.f;
+                for (int k = 0; k < kBins; ++k) { bins[a][k].reset(); cnt[a][k] = 0; }
+            }
+            for (uint32_t i = start; i < end; ++i) {
+                const PrimRef &p = prims[order[i]];
+                for (int a = 0; a < 3; ++a) {
+                    if (scale[a] == 0.f) continue;
+                    int k = std::min(kBins - 1, std::max(0, (int) ((p.c[a] - cbox.lo[a]) * scale[a])));
+                    bins[a][k].grow(p.b); cnt[a][k]++;
+                }
+            }
+            for (int a = 0; a < 3; ++a) {
+                if (scale[a] == 0.f) continue;
+                float ra[kBins]; uint32_t rc[kBins];
+                Box acc; acc.reset(); uint32_t c = 0;
+                for (int k = kBins - 1; k >= 0; --k) { if (cnt[a][k]) acc.grow(bins[a][k]); c += cnt[a][k]; ra[k] = acc.area(); rc[k] = c; }
+                acc.reset(); c = 0;
+                for (int k = 0; k < kBins - 1; ++k) {
+                    if (cnt[a][k]) acc.grow(bins[a][k]);
+                    c += cnt[a][k];
+                    if (c == 0 || rc[k + 1] == 0) continue;
+                    float cost = acc.area() * (float) c + ra[k + 1] * (float) rc[k + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+                }
+            }
+        }
+        uint32_t mid;
+        if (best_axis < 0) {
+            mid = start + n / 2;
+        } else {
+            const int a = best_axis;
+            const float sc = kBins / (cbox.hi[a] - cbox.lo[a]), lo = cbox.lo[a];
+            uint32_t *first = order + start, *last = order + end;
+            uint32_t *m = std::partition(first, last, [&](uint32_t id) {
+                int k = std::min(kBins - 1, std::max(0, (int) ((prims[id].c[a] - lo) * sc)));
+                return k <= best_bin;
+            });
+            mid = (uint32_t) (m - order);
+            if (mid == start || mid == end) mid = start + n / 2;
+        }
+        const uint32_t l = alloc(), r = alloc();
+        nodes[ni].left = l; nodes[ni].right = r;
+        bool spawned = false;
+        std::thread th;
+        if (n > 65536 && threads_free.load(std::memory_order_relaxed) > 0) {
+            if (threads_free.fetch_sub(1) > 0) {
+                spawned = true;
+                th = std::thread([this, l, start, mid, depth] { build(l, start, mid, depth + 1); });
+            } else {
+                threads_free.fetch_add(1);
+            }
+        }
+        if (!spawned) build(l, start, mid, depth + 1);
+        build(r, mid, end, depth + 1);
+        if (spawned) { th.join(); threads_free.fetch_add(1); }
+    }
+};
+
+inline float as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+}  // namespace
+
+void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_nodes, int nthreads) {
+    auto t0 = std::chrono::steady_clock::now();
+    max_leaf = std::min(8, std::max(1, max_leaf));
+    const uint32_t n = in.nprims;
+    std::vector<PrimRef> prims(n);
+    std::vector<uint32_t> order(n);
+    float maxabs = 0.f;
+    Box scene; scene.reset();
+    for (uint32_t i = 0; i < n; ++i) {
+        PrimRef &p = prims[i];
+        p.b.reset();
+        for (int k = 0; k < 3; ++k) {
+            const float *v = in.verts + 4 * (size_t) in.faces[4 * (size_t) i + k];
+            p.b.grow(v);
+            for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::fabs(v[a]));
+        }
+        for (int a = 0; a < 3; ++a) p.c[a] = 0.5f * (p.b.lo[a] + p.b.hi[a]);
+        scene.grow(p.b);
+        order[i] = i;
+    }
+    const float pad = 4e-6f * maxabs;
+    for (uint32_t i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) { prims[i].b.lo[a] -= pad; prims[i].b.hi[a] += pad; }
+    for (int a = 0; a < 3; ++a) { out.scene_lo[a] = n ? scene.lo[a] : 0.f; out.scene_hi[a] = n ? scene.hi[a] : 0.f; }
+
+    Builder b;
+    b.prims = prims.data(); b.order = order.data(); b.max_leaf = max_leaf;
+    b.nodes.resize(n ? 2 * (size_t) n : 1);
+    if (nthreads <= 0) nthreads = (int) std::thread::hardware_concurrency();
+    b.threads_free = std::max(0, nthreads - 1);
+    if (n) { uint32_t root = b.alloc(); b.build(root, 0, n, 0); }
+
+    // ---- relayout: inner nodes only; BFS for the first bfs_nodes, DFS below ----
+    out.nodes.clear(); out.tris.clear(); out.depth = 0;
+    auto absent = [&](float *nd, int c) {
+        if (c == 0) { nd[0] = kInf; nd[1] = -kInf; nd[2] = kInf; nd[3] = -kInf; nd[8] = kInf; nd[9] = -kInf; }
+        else { nd[4] = kInf; nd[5] = -kInf; nd[6] = kInf; nd[7] = -kInf; nd[10] = kInf; nd[11] = -kInf; }
+    };
+    auto put_box = [&](float *nd, int c, const Box &bx) {
+        if (c == 0) { nd[0] = bx.lo[0]; nd[1] = bx.hi[0]; nd[2] = bx.lo[1]; nd[3] = bx.hi[1]; nd[8] = bx.lo[2]; nd[9] = bx.hi[2]; }
+        else { nd[4] = bx.lo[0]; nd[5] = bx.hi[0]; nd[6] = bx.lo[1]; nd[7] = bx.hi[1]; nd[10] = bx.lo[2]; nd[11] = bx.hi[2]; }
+    };
+    auto emit_leaf = [&](const BNode &lf) -> int32_t {
+        const uint32_t first = (uint32_t) (out.tris.size() / 12);
+        for (uint32_t i = 0; i < lf.count; ++i) {
+            const uint32_t prim = order[lf.start + i];
+            for (int k = 0; k < 3; ++k) {
+                const float *v = in.verts + 4 * (size_t) in.faces[4 * (size_t) prim + k];
+                out.tris.push_back(v[0]); out.tris.push_back(v[1]); out.tris.push_back(v[2]);
+                out.tris.push_back(k == 0 ? as_float(prim) : 0.f);
+            }
+        }
+        return (int32_t) ~((first << 3) | (lf.count - 1));
+    };
+
+    if (n == 0 || b.nodes[0].count > 0) {
+        // degenerate trees: a root whose child 0 is the only leaf (or nothing at all)
+        out.nodes.assign(16, 0.f);
+        float *nd = out.nodes.data();
+        absent(nd, 0); absent(nd, 1);
+        int32_t r0 = -1, r1 = -1;   // never entered (inverted boxes)
+        if (n) { put_box(nd, 0, b.nodes[0].box); r0 = emit_leaf(b.nodes[0]); }
+        std::memcpy(&nd[12], &r0, 4); std::memcpy(&nd[13], &r1, 4);
+        out.nnodes = 1; out.top_nodes = 1; out.depth = 1;
+    } else {
+        // final index assignment
+        std::vector<uint32_t> final_order;   // build-node ids of inner nodes in final order
+        final_order.reserve(n);
+        std::vector<int32_t> final_index(b.nnodes.load(), -1);
+        std::vector<uint32_t> queue; queue.push_back(0);
+        size_t qh = 0;
+        while (qh < queue.size() && final_order.size() < bfs_nodes) {
+            uint32_t id = queue[qh++];
+            final_index[id] = (int32_t) final_order.size();
+            final_order.push_back(id);
+            const BNode &nd = b.nodes[id];
+            if (b.nodes[nd.left].count == 0) queue.push_back(nd.left);
+            if (b.nodes[nd.right].count == 0) queue.push_back(nd.right);
+        }
+        out.top_nodes = (uint32_t) final_order.size();
+        std::vector<uint32_t> stack;
+        for (size_t q = queue.size(); q-- > qh;) stack.push_back(queue[q]);   // remaining subtrees, DFS each (in queue order)
+        while (!stack.empty()) {
+            uint32_t id = stack.back(); stack.pop_back();
+            final_index[id] = (int32_t) final_order.size();
+            final_order.push_back(id);
+            const BNode &nd = b.nodes[id];
+            if (b.nodes[nd.right].count == 0) stack.push_back(nd.right);
+            if (b.nodes[nd.left].count == 0) stack.push_back(nd.left);
+        }
+        out.nnodes = (uint32_t) final_order.size();
+        out.nodes.assign((size_t) out.nnodes * 16, 0.f);
+        out.tris.reserve((size_t) n * 12);
+        for (uint32_t fi = 0; fi < out.nnodes; ++fi) {
+            const BNode &nd = b.nodes[final_order[fi]];
+            out.depth = std::max(out.depth, nd.depth + 2);
+            float *o = out.nodes.data() + (size_t) fi * 16;
+            const uint32_t ch[2] = { nd.left, nd.right };
+            for (int c = 0; c < 2; ++c) {
+                const BNode &cn = b.nodes[ch[c]];
+                put_box(o, c, cn.box);
+                int32_t ref = cn.count > 0 ? emit_leaf(cn) : final_index[ch[c]];
+                std::memcpy(&o[12 + c], &ref, 4);
+            }
+        }
+    }
+    out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace nb

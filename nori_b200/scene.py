@@ -336,7 +336,7 @@ def ajax_standin(levels: int = 4, seed: int = 7) -> Mesh:
     # place: the Ajax cameras sit at (-65.6, 47.6, 24.4) looking along (0.789, -0.355, -0.501)
     lo, hi = V.min(0), V.max(0)
     c = 0.5 * (lo + hi)
-    s = 36.0 / (hi[1] - lo[1])
+    s = 27.0 / (hi[1] - lo[1])
     V = (V - c) * s + np.array([-10.0, 20.0, -12.0])
     # turn the model to face the camera: rotate about y by ~ -50 degrees
     ang = math.radians(-58.0)

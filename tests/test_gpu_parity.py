@@ -1,0 +1,249 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.  Run on the B200 box: pytest -m gpu.
+
+Bars: bit-exact for integer/index results (hit triangle ids) and for fp32 hit records (the device code
+follows the oracle operation for operation, -fmad=false); films within 1e-4 relative L2 (BASELINE.json
+north_star) -- in practice ~1e-7, the residue of atomic accumulation order.
+"""
+import numpy as np
+import pytest
+
+from nori_b200 import abi
+from nori_b200 import scene as S
+from tests import fixtures as FX
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4   # north_star: <= 1e-4 rel-L2 vs the CPU reference at fixed pcg32 seeds
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = abi.Context(0)
+    yield c
+    c.close()
+
+
+def random_rays(n, lo, hi, seed=0, inward=True):
+    rng = np.random.default_rng(seed)
+    rays = np.zeros(n, dtype=abi.RAY_DTYPE)
+    c = 0.5 * (lo + hi); ext = float(np.max(hi - lo))
+    o = c + rng.normal(size=(n, 3)) * ext * 1.5
+    tgt = lo + rng.random((n, 3)) * (hi - lo)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["o"], rays["d"] = o.astype(np.float32), d.astype(np.float32)
+    rays["mint"], rays["maxt"] = 1e-4, np.inf
+    # a few axis-parallel and zero-component directions (the reference special-cases d == 0, bbox.h:331-333)
+    rays["d"][:6] = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1]]
+    rays["o"][:6] = (c - rays["d"][:6] * ext * 2).astype(np.float32)
+    return rays
+
+
+def test_intersect_bit_exact_vs_brute_force(ctx, oracle):
+    sc = S.config_bunny()
+    ctx.load(sc)
+    o = oracle.OracleScene(sc)
+    V = sc.meshes[0].V
+    rays = random_rays(200000, V.min(0), V.max(0))
+    gh, st = ctx.intersect(rays)
+    oh, _ = o.intersect(rays[:20000], accel=0)        # the reference's brute-force Accel
+    ob, _ = o.intersect(rays, accel=1)                # the oracle's own BVH
+    assert np.array_equal(gh["prim"][:20000], oh["prim"])
+    assert np.array_equal(gh[:20000].tobytes(), oh.tobytes())
+    assert np.array_equal(gh.tobytes(), ob.tobytes())
+    assert (gh["prim"] != 0xffffffff).mean() > 0.2
+    assert st.rays == rays.shape[0]
+    # shadow (any-hit) queries
+    gs, _ = ctx.intersect(rays, shadow=True)
+    os_, _ = o.intersect(rays, shadow=True, accel=1)
+    assert np.array_equal(gs["prim"], os_["prim"])
+    assert np.array_equal(gs["prim"] == 0, gh["prim"] != 0xffffffff)
+
+
+def test_intersect_edge_cases(ctx, oracle):
+    # empty ray batch, empty scene, single triangle, coincident duplicate triangles (tie -> highest index)
+    tri = S.Mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    cam = S.Camera(np.eye(4, dtype=np.float32), 30.0, 8, 8)
+    sc = S.Scene([tri, tri, tri], cam)
+    ctx.load(sc)
+    h, _ = ctx.intersect(np.zeros(0, dtype=abi.RAY_DTYPE))
+    assert h.shape[0] == 0
+    rays = np.zeros(3, dtype=abi.RAY_DTYPE)
+    rays["o"] = [[0.2, 0.2, 1], [0.2, 0.2, -1], [2, 2, 1]]
+    rays["d"] = [[0, 0, -1], [0, 0, 1], [0, 0, -1]]
+    rays["mint"], rays["maxt"] = 1e-4, np.inf
+    h, _ = ctx.intersect(rays)
+    oh, _ = oracle.OracleScene(sc).intersect(rays, accel=0)
+    assert list(h["prim"]) == [2, 2, 0xffffffff] and np.array_equal(h.tobytes(), oh.tobytes())
+    assert list(h["mesh"][:2]) == [2, 2]
+    # maxt clipping: hit beyond maxt is a miss, hit exactly at maxt counts (t <= maxt, ref: src/mesh.cpp:75)
+    rays["maxt"] = [0.5, 1.0, np.inf]
+    h, _ = ctx.intersect(rays)
+    assert list(h["prim"]) == [0xffffffff, 2, 0xffffffff]
+    empty = S.Scene([S.Mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))], cam)
+    ctx.load(empty)
+    h, _ = ctx.intersect(rays)
+    assert np.all(h["prim"] == 0xffffffff)
+    film, st = ctx.render()
+    assert np.all(film[..., :3] == 0) and st.samples == 64
+
+
+def test_hit_records_bit_exact(ctx, oracle):
+    for sc in (S.config_bunny(), S.config_cbox(64, 64, 1)):
+        ctx.load(sc)
+        o = oracle.OracleScene(sc)
+        lo = np.min([m.V.min(0) for m in sc.meshes], axis=0); hi = np.max([m.V.max(0) for m in sc.meshes], axis=0)
+        rays = random_rays(50000, lo, hi, seed=3)
+        g = ctx.intersect_full(rays)
+        r = o.intersect_full(rays, accel=1)
+        assert np.array_equal(g.tobytes(), r.tobytes())
+
+
+def _film_parity(ctx, oracle, sc, tol=TOL):
+    ctx.load(sc)
+    film, st = ctx.render()
+    ofilm, ost = oracle.OracleScene(sc).render(accel=1)
+    err = S.rel_l2(film, ofilm)
+    assert err <= tol, (sc.name, err)
+    assert st.samples == ost.samples and st.rays == ost.rays, (st.rays, ost.rays)
+    return err, film, ofilm
+
+
+def small_ajax(integrator, spp, w=160, h=120, levels=2, bsdf=None, light=False):
+    cam = S.Camera(S.lookat(**S._AJAX_CAM).astype(np.float32), 30.0, w, h)
+    meshes = [S.ajax_standin(levels)]
+    if bsdf is not None:
+        meshes[0] = S.with_(meshes[0], bsdf)
+    if light:
+        meshes.append(S.with_(S.golden_mesh("ajax_light"), S.diffuse(), radiance=(20, 20, 20)))
+    return S.Scene(meshes, cam, integrator, spp, name=f"small-ajax-{integrator}")
+
+
+def test_film_parity_normals_bunny(ctx, oracle):
+    sc = S.config_bunny(spp=4, seed_mode=S.SEED_PER_SAMPLE)
+    sc.camera.width = sc.camera.height = 192
+    err, film, _ = _film_parity(ctx, oracle, sc)
+    assert film[..., 3].min() >= 0 and film[..., :3].max() > 0
+
+
+def test_film_parity_reference_block_seeding(ctx, oracle):
+    """BASELINE configs[0]: scenes/pa1/bunny.xml as written -- 768x768, 1 spp, per-block pcg32 streams."""
+    _film_parity(ctx, oracle, S.config_bunny())
+
+
+def test_film_parity_ao(ctx, oracle):
+    _film_parity(ctx, oracle, small_ajax(S.INT_AO, 8))
+
+
+@pytest.mark.parametrize("integrator", ["whitted", "path_mats", "path_ems", "path_mis"])
+def test_film_parity_cbox(ctx, oracle, integrator):
+    _film_parity(ctx, oracle, S.config_cbox(64, 64, 16, S.INTEGRATORS[integrator]))
+
+
+def test_film_parity_cbox_specular(ctx, oracle):
+    sc = S.config_cbox(64, 64, 16, S.INT_PATH_MIS)
+    sc.meshes[3] = S.with_(sc.meshes[3], S.mirror())
+    sc.meshes[4] = S.with_(sc.meshes[4], S.dielectric())
+    _film_parity(ctx, oracle, sc)
+    sc.integrator = S.INT_WHITTED
+    _film_parity(ctx, oracle, sc)
+
+
+def test_film_parity_microfacet(ctx, oracle):
+    _film_parity(ctx, oracle, small_ajax(S.INT_PATH_MIS, 8, bsdf=S.microfacet((0.2, 0.2, 0.4), 0.28, 1.7), light=True))
+
+
+@pytest.mark.parametrize("table", ["tent", "box", "mitchell"])
+def test_film_parity_other_filters(ctx, oracle, table):
+    sc = small_ajax(S.INT_NORMALS, 2, 100, 70)   # ragged size: last tile row/column are partial
+    sc.filter_table, sc.filter_radius = getattr(S, table + "_table")()
+    _film_parity(ctx, oracle, sc)
+
+
+def test_tile_sharding_sums_to_full_frame(ctx, oracle):
+    sc = small_ajax(S.INT_AO, 4, 200, 136)
+    ctx.load(sc)
+    full, st_full = ctx.render()
+    acc = np.zeros_like(full); samples = 0
+    for r in range(3):
+        ctx.set_tiles(r, 3)
+        part, st = ctx.render()
+        acc += part; samples += st.samples
+    ctx.set_tiles(0, 1)
+    assert samples == st_full.samples == 200 * 136 * 4
+    assert S.rel_l2(acc, full) < 1e-6
+    o = oracle.OracleScene(sc); o.set_tiles(1, 3)
+    ctx.set_tiles(1, 3); part, _ = ctx.render(); ctx.set_tiles(0, 1)
+    opart, _ = o.render()
+    assert S.rel_l2(part, opart) < TOL
+
+
+def test_render_is_deterministic_in_counts_and_film(ctx):
+    sc = small_ajax(S.INT_PATH_MIS, 4, light=True)
+    ctx.load(sc)
+    a, sa = ctx.render(); b, sb = ctx.render()
+    assert sa.rays == sb.rays and S.rel_l2(a, b) < 1e-6
+
+
+def test_instrumented_counts_match_plain(ctx):
+    sc = small_ajax(S.INT_AO, 4)
+    ctx.load(sc)
+    a, sa = ctx.render()
+    ctx.set_option("count", 1)
+    b, sb = ctx.render()
+    ctx.set_option("count", 0)
+    assert sa.rays == sb.rays and sb.node_visits > 0 and sb.tri_tests > 0 and S.rel_l2(a, b) < 1e-6
+
+
+@pytest.mark.parametrize("opt,val", [("smem_nodes", 512), ("refill_threshold", 1), ("refill_threshold", 32), ("chunk", 1), ("blocks_per_sm", 1)])
+def test_tuning_options_do_not_change_results(ctx, oracle, opt, val):
+    sc = small_ajax(S.INT_AO, 4)
+    ctx.load(sc)
+    ref, _ = ctx.render()
+    ctx.set_option(opt, val)
+    try:
+        got, _ = ctx.render()
+    finally:
+        ctx.set_option(opt, {"smem_nodes": 0, "refill_threshold": 8, "chunk": 16, "blocks_per_sm": 0}[opt])
+    assert S.rel_l2(got, ref) < 1e-6
+
+
+@pytest.mark.parametrize("integrator", ["whitted", "path_ems", "path_mats", "path_mis"])
+def test_reference_fixtures_on_gpu(ctx, oracle, integrator):
+    """The reference's polygon-light and furnace known answers, evaluated by the CUDA path (1x1 px, box filter,
+    100k spp -> film pixel = sample mean); z-test with the variance estimated by the oracle's sample set."""
+    n = 100000
+    cases = [(FX.polylum_scene(i, S.INTEGRATORS[integrator]), ref) for i, ref in enumerate(FX.POLYLUM_REFS, 1)]
+    cases += [(FX.furnace_scene(a, S.INTEGRATORS[integrator]), r) for a, r in
+              ([(0.5, 1.5), (0.8, 1.8)] if integrator == "whitted" else [(0.5, 2.0), (0.8, 5.0)])]
+    thr = FX.sidak(FX.SIGNIFICANCE, len(cases))
+    from scipy import stats
+    for sc, ref in cases:
+        sc.spp = n
+        sc.filter_table, sc.filter_radius = S.box_table()
+        ctx.load(sc)
+        film, _ = ctx.render()
+        rgb = ctx.film_to_rgb(film)
+        mean = float(rgb[0, 0] @ np.array([0.212671, 0.715160, 0.072169]))
+        lum = oracle.OracleScene(sc).ttest_lum(20000)
+        sd = max(float(lum.std(ddof=1)), 1e-6)
+        z = abs(mean - ref) * np.sqrt(n) / sd
+        assert 2 * stats.norm.sf(z) > thr, (sc.name, integrator, mean, ref)
+
+
+def test_full_size_config1_parity_and_properties(ctx, oracle):
+    """BASELINE configs[1] at full size (800x600x64 AO on the Ajax stand-in): film parity with the oracle, plus
+    size-independent properties: the weight channel does not depend on the integrator, AO values lie in [0,1]."""
+    sc = S.config_ajax_ao()
+    ctx.load(sc)
+    film, st = ctx.render()
+    rgb = ctx.film_to_rgb(film)
+    assert st.samples == 800 * 600 * 64
+    assert rgb.min() >= 0.0 and rgb.max() <= 1.0 + 1e-5
+    ofilm, ost = oracle.OracleScene(sc).render(accel=1)
+    assert st.rays == ost.rays
+    assert S.rel_l2(film, ofilm) <= TOL
+    assert S.rel_l2(rgb, oracle.film_to_rgb(ofilm, 800, 600, sc.border)) <= TOL
+    sc.integrator = S.INT_NORMALS
+    ctx.configure(sc)
+    film2, _ = ctx.render()
+    assert S.rel_l2(film2[..., 3], film[..., 3]) < 1e-6
