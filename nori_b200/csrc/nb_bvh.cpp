@@ -160,9 +160,9 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
 
     // ---- relayout: inner nodes only; BFS for the first bfs_nodes, DFS below ----
     out.nodes.clear(); out.tris.clear(); out.depth = 0;
-    auto absent = [&](float *nd, int c) {
-        if (c == 0) { nd[0] = kInf; nd[1] = -kInf; nd[2] = kInf; nd[3] = -kInf; nd[8] = kInf; nd[9] = -kInf; }
-        else { nd[4] = kInf; nd[5] = -kInf; nd[6] = kInf; nd[7] = -kInf; nd[10] = kInf; nd[11] = -kInf; }
+    auto absent = [&](float *nd, int c) {   // degenerate point box at the origin (the leaf behind it rejects everything)
+        if (c == 0) { nd[0] = nd[1] = nd[2] = nd[3] = nd[8] = nd[9] = 0.f; }
+        else { nd[4] = nd[5] = nd[6] = nd[7] = nd[10] = nd[11] = 0.f; }
     };
     auto put_box = [&](float *nd, int c, const Box &bx) {
         if (c == 0) { nd[0] = bx.lo[0]; nd[1] = bx.hi[0]; nd[2] = bx.lo[1]; nd[3] = bx.hi[1]; nd[8] = bx.lo[2]; nd[9] = bx.hi[2]; }
@@ -186,8 +186,14 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
         out.nodes.assign(16, 0.f);
         float *nd = out.nodes.data();
         absent(nd, 0); absent(nd, 1);
-        int32_t r0 = -1, r1 = -1;   // never entered (inverted boxes)
+        // An absent child is a one-triangle leaf holding a degenerate (all-zero) triangle: det == 0, always rejected
+        // (ref: src/mesh.cpp:52).  (An inverted box would NOT be culled by a min/max slab test.)
+        int32_t r0, r1;
         if (n) { put_box(nd, 0, b.nodes[0].box); r0 = emit_leaf(b.nodes[0]); }
+        const uint32_t dummy = (uint32_t) (out.tris.size() / 12);
+        for (int k = 0; k < 12; ++k) out.tris.push_back(0.f);
+        r1 = (int32_t) ~((dummy << 3) | 0u);
+        if (!n) r0 = r1;
         std::memcpy(&nd[12], &r0, 4); std::memcpy(&nd[13], &r1, 4);
         out.nnodes = 1; out.top_nodes = 1; out.depth = 1;
     } else {

@@ -8,7 +8,8 @@
 //             n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
 //             n3 = (ref0, ref1, 0, 0) as int bits; ref >= 0: inner node index,
 //                  ref < 0: leaf, ~ref = (first_leaf_triangle << 3) | (count - 1), count in 1..8
-//           an absent child has an inverted box (lo=+inf, hi=-inf) and is never entered.
+//           an absent child (trees with < 2 leaves) is a leaf holding one degenerate all-zero triangle, which
+//           Moeller-Trumbore always rejects (det == 0).
 //   tris  : 48 B per leaf-ordered triangle = 3 x float4 = (p0.xyz, prim_id bits), (p1.xyz, 0), (p2.xyz, 0)
 //           -- exactly the 12 B of indices + 36 B of vertices Mesh::rayIntersect reads (ref: src/mesh.cpp:40-41),
 //           pre-gathered so a leaf is one contiguous stream.
