@@ -12,7 +12,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnori_b200.so")
+LIB_PATH = os.environ.get("NORI_B200_LIB") or os.path.join(_HERE, "lib", "libnori_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nori_b200.h")
 
 

@@ -41,14 +41,14 @@ def _run(cmd, log_name):
     return r
 
 
-def build_cuda(force=False):
+def build_cuda(force=False, variant="", extra_flags=()):
     os.makedirs(LIB, exist_ok=True)
-    target = os.path.join(LIB, "libnori_b200.so")
+    target = os.path.join(LIB, f"libnori_b200{variant}.so")
     srcs = [os.path.join(CSRC, f) for f in ("nb_api.cu", "nb_bvh.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("nb_bvh.h", "nb_kernels.cuh", "nb_device.cuh")] + \
         [os.path.join(os.path.dirname(HERE), "include", "nori_b200.h")]
     if force or _stale(target, deps):
-        _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", target] + srcs, "build_cuda.log")
+        _run([NVCC] + NVCC_FLAGS + list(extra_flags) + ["-shared", "-o", target] + srcs, f"build_cuda{variant}.log")
     return target
 
 
@@ -63,11 +63,11 @@ def build_host(force=False):
     inc = ["-I", host, "-I", os.path.join(os.path.dirname(HERE), "include")]
     flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-pthread"]
     if force or _stale(target, srcs + hdrs):
-        _run(["g++"] + flags + inc + ["-shared", "-o", target] + srcs + ["-ldl"], "build_host.log")
+        _run(["g++"] + flags + inc + ["-shared", "-o", target] + srcs + ["-L", LIB, "-lnori_b200", "-ldl", "-Wl,-rpath,$ORIGIN"], "build_host.log")
     exe = os.path.join(LIB, "nori")
     main = os.path.join(host, "main.cpp")
     if os.path.exists(main) and (force or _stale(exe, [main, target] + hdrs)):
-        _run(["g++"] + flags + inc + ["-o", exe, main, "-L", LIB, "-lnori_host", "-ldl", "-Wl,-rpath,$ORIGIN"], "build_cli.log")
+        _run(["g++"] + flags + inc + ["-o", exe, main, "-L", LIB, "-lnori_host", "-lnori_b200", "-ldl", "-Wl,-rpath,$ORIGIN"], "build_cli.log")
     return target
 
 

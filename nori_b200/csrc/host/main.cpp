@@ -1,0 +1,46 @@
+// main.cpp -- `nori <scene.xml>` command line (ref: src/main.cpp:150-246).  --no-gui / --threads are accepted for
+// compatibility and ignored (there is no GUI and no TBB on this path); --device N selects the GPU.
+#include <cstring>
+#include "nori/parser.h"
+#include "nori/render.h"
+
+using namespace nori;
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N]" << endl;
+        return -1;
+    }
+    std::string sceneName;
+    RenderOptions opt;
+    for (int i = 1; i < argc; ++i) {
+        std::string token(argv[i]);
+        if (token == "-t" || token == "--threads") {
+            if (i + 1 >= argc) { cerr << "\"--threads\" argument expects a positive integer following it." << endl; return -1; }
+            ++i;   // accepted, unused
+        } else if (token == "--no-gui") {
+        } else if (token == "--device") {
+            if (i + 1 >= argc) { cerr << "\"--device\" expects an integer following it." << endl; return -1; }
+            opt.device = atoi(argv[++i]);
+        } else {
+            sceneName = token;
+        }
+    }
+    try {
+        if (endsWith(toLower(sceneName), ".xml")) {
+            std::unique_ptr<NoriObject> root(loadFromXML(sceneName));
+            /* When the XML root object is a scene, start rendering it (ref: src/main.cpp:236-238) */
+            if (root->getClassType() == NoriObject::EScene) {
+                cout << endl << "Configuration: " << root->toString() << endl << endl;
+                render(static_cast<Scene *>(root.get()), sceneName, opt);
+            }
+        } else {
+            cerr << "Fatal error: unknown file \"" << sceneName << "\", expected an extension of type .xml" << endl;
+            return -1;
+        }
+    } catch (const std::exception &e) {
+        cerr << "Fatal error: " << e.what() << endl;
+        return -1;
+    }
+    return 0;
+}

@@ -1,0 +1,27 @@
+// render.h -- the render() driver of the host (ref: src/main.cpp:58-148) on top of the C-ABI in include/nori_b200.h.
+#pragma once
+#include "block.h"
+#include "scene.h"
+
+struct nb_ctx;
+struct nb_stats;
+
+NORI_NAMESPACE_BEGIN
+
+struct RenderOptions {
+    int device = 0;            // CUDA device of this process
+    int tileRank = 0, tileRanks = 1;   // tile shard (multi-GPU: one process per GPU)
+    bool quiet = false;
+};
+
+/// Builds the GPU context for a scene: meshes + plugin descriptors (from the factory's creation records), BVH,
+/// camera, tabulated filter, sampler, integrator.  Throws NoriException on anything the device path cannot run.
+nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const RenderOptions &opt);
+
+/// Replaces the body of render(): fills `result` (the full-image ImageBlock) through nb_render.
+void renderScene(Scene *scene, ImageBlock &result, const RenderOptions &opt, nb_stats *stats = nullptr);
+
+/// Full driver: render + toBitmap + EXR/PNG next to the scene file (ref: src/main.cpp:127-147)
+void render(Scene *scene, const std::string &filename, const RenderOptions &opt);
+
+NORI_NAMESPACE_END

@@ -76,7 +76,7 @@ struct nb_ctx {
     unsigned long long *counters = nullptr;          // 8 x u64 device
     unsigned long long *counters_h = nullptr;        // pinned
     // options
-    int64_t opt_blocks_per_sm = 0, opt_refill = 8, opt_smem_nodes = 0, opt_chunk = 16, opt_count = 0, opt_max_leaf = 4,
+    int64_t opt_blocks_per_sm = 0, opt_refill = 32, opt_smem_nodes = 0, opt_chunk = 8, opt_count = 0, opt_max_leaf = 4,
             opt_bfs_nodes = 2048;
 };
 
@@ -107,20 +107,23 @@ void launch_render(const nb::RenderParams &P, bool count, bool block_mode, int g
         if (count) nb::render_block_mode_kernel<INTEG, true><<<g, 32, 0, s>>>(P);
         else nb::render_block_mode_kernel<INTEG, false><<<g, 32, 0, s>>>(P);
     } else {
-        if (count) nb::render_kernel<INTEG, true><<<grid, 128, smem, s>>>(P);
-        else nb::render_kernel<INTEG, false><<<grid, 128, smem, s>>>(P);
+        if (count) nb::render_kernel<INTEG, true, false><<<grid, 128, smem, s>>>(P);
+        else if (P.smem_nodes > 0) nb::render_kernel<INTEG, false, true><<<grid, 128, smem, s>>>(P);
+        else nb::render_kernel<INTEG, false, false><<<grid, 128, smem, s>>>(P);
     }
 }
 
 template <int INTEG>
-cudaError_t occupancy(int *blocks, bool count, size_t smem) {
+cudaError_t occupancy(int *blocks, bool count, bool tma, size_t smem) {
+    auto kc = nb::render_kernel<INTEG, true, false>;
+    auto kt = nb::render_kernel<INTEG, false, true>;
+    auto kp = nb::render_kernel<INTEG, false, false>;
+    auto k = count ? kc : (tma ? kt : kp);
     if (smem > 48 * 1024) {
-        cudaError_t e = count ? cudaFuncSetAttribute(nb::render_kernel<INTEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)
-                              : cudaFuncSetAttribute(nb::render_kernel<INTEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
     }
-    return count ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, nb::render_kernel<INTEG, true>, 128, smem)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, nb::render_kernel<INTEG, false>, 128, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k, 128, smem);
 }
 
 // Renders this context's tiles into c->blocks (or blocks_out) on stream s.
@@ -162,16 +165,17 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     P.counters = c->counters;
     P.refill_threshold = (int) std::max<int64_t>(1, std::min<int64_t>(32, c->opt_refill));
     const bool block_mode = c->seed_mode == NB_SEED_PER_BLOCK;
-    P.smem_nodes = block_mode ? 0 : (int) std::min<int64_t>(std::min<int64_t>(c->opt_smem_nodes, c->top_nodes), 3400);
-    const size_t smem = (size_t) P.smem_nodes * 64;
     const bool count = c->opt_count != 0;
+    P.smem_nodes = (block_mode || count) ? 0 : (int) std::min<int64_t>(std::min<int64_t>(c->opt_smem_nodes, c->top_nodes), 3400);
+    const size_t smem = (size_t) P.smem_nodes * 64;
+    P.step_budget = P.refill_threshold >= 32 ? (1 << 30) : 24;
 
     int occ = 0;
     cudaError_t oe = cudaSuccess;
     switch (c->integ.type) {
-        case 0: oe = occupancy<0>(&occ, count, smem); break; case 1: oe = occupancy<1>(&occ, count, smem); break;
-        case 2: oe = occupancy<2>(&occ, count, smem); break; case 3: oe = occupancy<3>(&occ, count, smem); break;
-        case 4: oe = occupancy<4>(&occ, count, smem); break; default: oe = occupancy<5>(&occ, count, smem); break;
+        case 0: oe = occupancy<0>(&occ, count, P.smem_nodes > 0, smem); break; case 1: oe = occupancy<1>(&occ, count, P.smem_nodes > 0, smem); break;
+        case 2: oe = occupancy<2>(&occ, count, P.smem_nodes > 0, smem); break; case 3: oe = occupancy<3>(&occ, count, P.smem_nodes > 0, smem); break;
+        case 4: oe = occupancy<4>(&occ, count, P.smem_nodes > 0, smem); break; default: oe = occupancy<5>(&occ, count, P.smem_nodes > 0, smem); break;
     }
     if (oe != cudaSuccess) return fail("occupancy query failed: %s", cudaGetErrorString(oe));
     if (occ < 1) return fail("render kernel does not fit on an SM (smem %zu B)", smem);

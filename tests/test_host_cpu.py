@@ -1,0 +1,112 @@
+"""The C++ host mirror of Nori (NoriObject registry, PropertyList, XML parser, OBJ loader, plugins) -- CPU-only checks.
+Error behaviour follows the reference (exceptions with the same messages, ref: include/nori/object.h:132-133,
+src/parser.cpp:105-116,183-190, src/scene.cpp:64-76)."""
+import os
+
+import numpy as np
+import pytest
+
+from nori_b200 import abi, host
+from nori_b200 import scene as S
+
+
+def test_every_hot_path_plugin_is_registered():
+    names = ["scene", "obj", "diffuse", "mirror", "dielectric", "microfacet", "area", "independent", "perspective",
+             "gaussian", "mitchell", "tent", "box", "normals", "ao", "whitted", "path_mats", "path_ems", "path_mis"]
+    assert all(host.is_registered(n) for n in names)
+    assert not host.is_registered("photonmapper")
+
+
+def test_xml_pipeline_matches_python_description(tmp_path):
+    sc = S.config_cbox(64, 48, 7, S.INT_PATH_MIS)
+    sc.meshes[3] = S.with_(sc.meshes[3], S.microfacet((0.2, 0.2, 0.4), 0.28, 1.7))
+    sc.meshes[4] = S.with_(sc.meshes[4], S.dielectric(1.33, 1.0))
+    path = host.write_xml(sc, str(tmp_path), "cbox")
+    hs = host.HostScene(path)
+    info = hs.info()
+    assert info == dict(width=64, height=48, border=2, spp=7, n_meshes=6, n_triangles=sc.n_tris, integrator=S.INT_PATH_MIS, seed_mode=0)
+    cam = hs.camera()
+    assert np.allclose(cam["s2c"], sc.camera.s2c, rtol=2e-6, atol=1e-9)
+    assert np.array_equal(cam["c2w"], sc.camera.c2w)
+    assert cam["filter_radius"] == 2.0 and np.allclose(cam["filter_table"], sc.filter_table, rtol=1e-6, atol=1e-9)
+    for i, m in enumerate(sc.meshes):
+        hm = hs.mesh(i)
+        assert np.array_equal(hm["V"], m.V) and np.array_equal(hm["F"], m.F)
+        assert (hm["N"] is None) == (m.N is None) and (hm["UV"] is None) == (m.UV is None)
+        if m.N is not None:
+            assert np.allclose(hm["N"], m.N, atol=1e-6)
+        assert hm["bsdf"]["type"] == m.bsdf.type
+        assert np.allclose(hm["bsdf"]["albedo"], np.float32(m.bsdf.albedo)) or m.bsdf.type in (S.BSDF_MIRROR, S.BSDF_DIELECTRIC)
+        assert (hm["emitter"]["type"] == 1) == (m.radiance is not None)
+    assert hs.mesh(3)["bsdf"]["ks"] == pytest.approx(0.6) and hs.mesh(3)["bsdf"]["alpha"] == pytest.approx(0.28)
+    assert hs.mesh(4)["bsdf"]["intIOR"] == pytest.approx(1.33)
+    assert hs.mesh(5)["emitter"]["radiance"] == (40.0, 40.0, 40.0)
+
+
+def test_obj_loader_rules(tmp_path):
+    """v/vt/vn/f, quad split (0,1,2),(3,0,2), dedup on the (p,uv,n) triple in first-use order, toWorld (ref: src/obj.cpp:43-112)."""
+    (tmp_path / "q.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                                    "f 1/1/1 2/2/1 3/3/1 4/4/1\nf 1/2/1 2/2/1 3/3/1\n")
+    (tmp_path / "s.xml").write_text("""<scene><integrator type="normals"/><camera type="perspective"/>
+      <mesh type="obj"><string name="filename" value="q.obj"/>
+        <transform name="toWorld"><scale value="2,2,2"/><translate value="1,0,0"/></transform></mesh></scene>""")
+    hs = host.HostScene(str(tmp_path / "s.xml"))
+    m = hs.mesh(0)
+    ref = S.load_obj(str(tmp_path / "q.obj"), S.translate([1, 0, 0]) @ S.scale([2, 2, 2]))
+    assert np.array_equal(m["F"], ref.F) and m["F"].tolist() == [[0, 1, 2], [3, 0, 2], [4, 1, 2]]
+    assert np.allclose(m["V"], ref.V) and np.allclose(m["V"][2], [3, 2, 0])
+    assert np.allclose(m["UV"], ref.UV) and np.allclose(m["N"], ref.N)
+    assert m["bsdf"]["type"] == S.BSDF_DIFFUSE and m["bsdf"]["albedo"] == (0.5, 0.5, 0.5)    # default BSDF (ref: src/mesh.cpp:23-29)
+    i = hs.info()
+    assert (i["width"], i["height"], i["spp"]) == (1280, 720, 1)                          # camera / sampler defaults
+
+
+def test_lookat_rotate_and_defaults(tmp_path):
+    (tmp_path / "t.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    (tmp_path / "s.xml").write_text("""<?xml version="1.0"?><!-- c --><scene><integrator type="ao"/>
+      <camera type="perspective"><transform name="toWorld"><rotate angle="90" axis="0,0,1"/>
+        <lookat origin="1,2,3" target="0,0,0" up="0,1,0"/></transform>
+        <rfilter type="tent"/></camera>
+      <mesh type="obj"><string name="filename" value="t.obj"/></mesh></scene>""")
+    cam = host.HostScene(str(tmp_path / "s.xml")).camera()
+    c, s = np.cos(np.pi / 2), np.sin(np.pi / 2)
+    R = np.array([[c, -s, 0, 0], [s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    assert np.allclose(cam["c2w"], S.lookat([1, 2, 3], [0, 0, 0], [0, 1, 0]) @ R, atol=1e-6)
+    assert cam["filter_radius"] == 1.0 and np.allclose(cam["filter_table"], S.tent_table()[0])
+
+
+@pytest.mark.parametrize("xml,msg", [
+    ('<scene><integrator type="photonmapper"/></scene>', 'A constructor for class "photonmapper" could not be found!'),
+    ('<scene><integrator type="ao" foo="1"/></scene>', 'unexpected attribute "foo"'),
+    ('<scene><integrator/></scene>', 'missing attribute "type"'),
+    ('<scene><camera type="perspective"/></scene>', "No integrator was specified!"),
+    ('<scene><integrator type="ao"/><camera type="perspective"/><camera type="perspective"/></scene>', "There can only be one camera per scene!"),
+    ('<scene><integrator type="ao"/><camera type="ao"/></scene>', "Unexpectedly constructed an object of type <integrator>"),
+    ('<scene><integrator type="ao"/><float name="x" value="1.0abc"/></scene>', 'Could not parse floating point value "1.0abc"'),
+    ('<scene><integrator type="ao"/><translate value="1,2,3"/></scene>', "transform nodes can only contain transform operations"),
+    ('<float name="x" value="1"/>', "must be a Nori object"),
+    ('<scene><integrator type="ao"></scene>', "mismatched closing tag"),
+    ('<scene><mesh type="obj"><string name="filename" value="missing.obj"/></mesh></scene>', "Unable to open OBJ file"),
+    ('<scene><mesh type="obj"><emitter type="area"/></mesh></scene>', "Property 'radiance' is missing!"),
+])
+def test_parser_errors(tmp_path, xml, msg):
+    p = tmp_path / "bad.xml"
+    p.write_text(xml)
+    with pytest.raises(abi.NoriError) as e:
+        host.HostScene(str(p))
+    assert msg in str(e.value) and "Error while parsing" in str(e.value)
+
+
+def test_block_generator_spiral_matches_oracle(oracle):
+    """BlockGenerator order (ref: src/block.cpp:109-152): host C++ class == oracle restatement; sizes clip at the edges."""
+    import ctypes as C
+    for W, H in [(768, 768), (800, 600), (100, 70), (31, 33), (1, 1)]:
+        hb = host.block_order(W, H)
+        n = oracle.lib().orc_block_order(W, H, 32, None)
+        xy = np.zeros((n, 2), dtype=np.int32)
+        oracle.lib().orc_block_order(W, H, 32, xy.ctypes.data_as(C.c_void_p))
+        assert hb.shape[0] == n == ((W + 31) // 32) * ((H + 31) // 32)
+        assert np.array_equal(hb[:, :2], xy * 32)
+        assert np.all(hb[:, 2] == np.minimum(32, W - hb[:, 0])) and np.all(hb[:, 3] == np.minimum(32, H - hb[:, 1]))
+        assert len({(int(a), int(b)) for a, b in hb[:, :2]}) == n
+    assert host.block_order(768, 768)[0, :2].tolist() == [384, 384]        # starts at the centre block
