@@ -163,7 +163,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from nori_b200 import abi
+    from nori_b200 import abi, multigpu as MG
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback (use --impl reference for the CPU arm)")
@@ -190,22 +190,17 @@ def main():
 
     blocks = torch.zeros((n_max, edge, edge, 4), dtype=torch.float32, device=dev)
     film = torch.zeros((H2, W2, 4), dtype=torch.float32, device=dev)
-    gathered = [torch.zeros_like(blocks) for _ in range(world)] if (rank == 0 and world > 1) else None
     film_host = torch.zeros((H2, W2, 4), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def step_device():
         """render my tiles -> (gather finished blocks over NCCL) -> merge into the film on rank 0."""
         st = ctx.render_blocks_device(blocks.data_ptr(), stream)
-        if world > 1:
-            dist.gather(blocks, gathered, dst=0)
+        gathered = MG.gather_blocks(blocks, world, rank, dst=0)      # ONE exchange per frame (NCCL send/recv over NVLink)
         if rank == 0:
             film.zero_()
-            if world > 1:
-                for r in range(world):
-                    ctx.merge_blocks_device(gathered[r].data_ptr(), r, world, film.data_ptr(), stream)
-            else:
-                ctx.merge_blocks_device(blocks.data_ptr(), 0, 1, film.data_ptr(), stream)
+            for r in range(world):
+                ctx.merge_blocks_device(gathered[r].data_ptr(), r, world, film.data_ptr(), stream)
         return st
 
     def barrier():
