@@ -76,7 +76,7 @@ struct nb_ctx {
     unsigned long long *counters = nullptr;          // 8 x u64 device
     unsigned long long *counters_h = nullptr;        // pinned
     // options
-    int64_t opt_blocks_per_sm = 0, opt_refill = 32, opt_smem_nodes = 0, opt_chunk = 8, opt_count = 0, opt_max_leaf = 4,
+    int64_t opt_blocks_per_sm = 0, opt_refill = 32, opt_smem_nodes = 0, opt_chunk = 8, opt_count = 0, opt_max_leaf = 3,
             opt_bfs_nodes = 2048;
 };
 

@@ -28,8 +28,13 @@ def main():
         axes.append([(k, int(v)) for v in vs.split(",")])
     defaults = {"blocks_per_sm": 0, "refill_threshold": 32, "smem_nodes": 0, "chunk": 4}
     for combo in itertools.product(*axes):
+        rebuild = False
         for k, v in combo:
             ctx.set_option(k, v)
+            rebuild |= k in ("max_leaf", "bfs_nodes")
+        if rebuild:
+            ctx.load(sc)
+            print(json.dumps({"rebuilt": dict(combo), **ctx.scene_info()}))
         ctx.render()
         ms = []
         for _ in range(a.reps):
