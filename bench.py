@@ -97,6 +97,15 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload (None if not captured)."""
+    p = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(workload, {}).get("bytes")
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(st, scene):
     """64 B per BVH node visit + 48 B per triangle test + 36 B of normals per shaded closest hit
     (+24 B UVs when present) + one film write; rays are generated and consumed in registers (0 B)."""
@@ -150,7 +159,7 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--tris", type=int, default=0)
-    ap.add_argument("--ref-spp", type=int, default=16, help="spp per step of the CPU arm (bounded sample)")
+    ap.add_argument("--ref-spp", type=int, default=32, help="spp per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="key=value tuning option (nb_set_option)")
     args = ap.parse_args()
@@ -298,7 +307,7 @@ def main():
                     "what": "nb_upload_scene (scene arrays from pinned host memory) + nb_render into a host film"},
             "gpu_launches": int(args.steps * 2 * world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "render_kernel<ao>",
+                         "traffic": ncu_traffic(args.workload) if world == 1 else None, "peak_source": peak_src, "kernel": "render_kernel<ao>",
                          "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_launch": alg_bytes / world,
                          "node_visits": tot_nodes, "tri_tests": tot_tris, "hits_shaded": tot_hits,
                          "note": "scene (%.0f MB) is L2-resident: this is EFFECTIVE bandwidth of the traversal, see profiles/ for DRAM bytes" % (info["bytes"] / 1e6)},

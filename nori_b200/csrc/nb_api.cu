@@ -76,7 +76,7 @@ struct nb_ctx {
     unsigned long long *counters = nullptr;          // 8 x u64 device
     unsigned long long *counters_h = nullptr;        // pinned
     // options
-    int64_t opt_blocks_per_sm = 0, opt_refill = 32, opt_smem_nodes = 0, opt_chunk = 8, opt_count = 0, opt_max_leaf = 3,
+    int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 8, opt_count = 0, opt_max_leaf = 3,
             opt_bfs_nodes = 2048;
 };
 
@@ -163,12 +163,10 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     }
     P.blocks = blocks_out;
     P.counters = c->counters;
-    P.refill_threshold = (int) std::max<int64_t>(1, std::min<int64_t>(32, c->opt_refill));
     const bool block_mode = c->seed_mode == NB_SEED_PER_BLOCK;
     const bool count = c->opt_count != 0;
     P.smem_nodes = (block_mode || count) ? 0 : (int) std::min<int64_t>(std::min<int64_t>(c->opt_smem_nodes, c->top_nodes), 3400);
     const size_t smem = (size_t) P.smem_nodes * 64;
-    P.step_budget = P.refill_threshold >= 32 ? (1 << 30) : 24;
 
     int occ = 0;
     cudaError_t oe = cudaSuccess;
@@ -564,7 +562,6 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail("null argument");
     std::string k(key);
     if (k == "blocks_per_sm") c->opt_blocks_per_sm = value;
-    else if (k == "refill_threshold") c->opt_refill = value;
     else if (k == "smem_nodes") c->opt_smem_nodes = value;
     else if (k == "chunk") c->opt_chunk = value;
     else if (k == "count") c->opt_count = value;

@@ -7,12 +7,13 @@
 //   K5 film splat  : ImageBlock::put(pos, value)                  (ref: src/block.cpp:62-91)
 //   K6 film merge  : ImageBlock::put(block)                       (ref: src/block.cpp:93-102)
 //
-// K1..K5 are fused into ONE persistent-threads kernel (render_kernel): every lane owns one light path
-// at a time; the warp alternates between a traversal phase (while-while BVH walk, per-lane stack) and a
-// shading phase that runs when enough lanes have finished their ray (ballot count), after which finished
-// paths are replaced from a warp-local pool of (pixel, sample) items refilled from a global atomic
-// counter (ballot/popc compaction of the free lanes).  Rays never leave registers.
-// The top of the BVH is staged into shared memory once per CTA with a TMA bulk copy (cp.async.bulk).
+// K1..K5 are fused into ONE persistent-threads kernel (render_kernel): every lane owns one light path at a
+// time.  The warp runs in lock step over RAYS: a shading phase in which all 32 lanes advance their path by one
+// vertex (hit record, integrator step, next ray; finished paths are splatted and replaced from a warp-local
+// pool of (pixel, sample) items refilled from a global atomic counter, free lanes ranked by ballot/popc), then a
+// traversal phase in which every lane walks its ray through the BVH to completion (while-while, per-lane stack,
+// speculative: a found leaf is parked while the lane keeps descending).  Rays never leave registers.
+// Optionally the top of the BVH is staged into shared memory once per CTA with a TMA bulk copy (cp.async.bulk).
 #pragma once
 #include "nb_device.cuh"
 
@@ -61,9 +62,7 @@ struct RenderParams {
     uint32_t n_units;
     float4 *blocks;                 // n_my_tiles x block_edge x block_edge
     unsigned long long *counters;   // [0] next unit, [1] rays, [2] node visits, [3] tri tests, [4] hits shaded
-    int32_t refill_threshold;       // lanes that must be waiting before the warp shades
     int32_t smem_nodes;             // nodes staged in shared memory (0 = none)
-    int32_t step_budget;            // node visits a lane may take before the warp re-votes
 };
 
 // ------------------------------------------------------------------ traversal state (per lane)
@@ -98,19 +97,57 @@ __device__ __forceinline__ float4 ld_node(const SceneDev &sc, const float4 *snod
     return __ldg(&sc.nodes[(size_t) node * 4 + k]);
 }
 
-// Runs the while-while walk for at most `budget` node visits.  Returns true when the ray is finished.
+// The while-while BVH walk of one ray, run to completion.
 // any_hit: stop at the first accepted triangle (Accel::rayIntersect(..., shadowRay=true), ref: src/accel.cpp:35-36).
 // Closest hit keeps shrinking r.maxt (ref: src/accel.cpp:37); among equal t the highest triangle index wins,
-// which is what the reference's ascending loop with "t <= maxt" produces (ref: src/mesh.cpp:75).
+// which is what the reference's ascending loop with "t <= maxt" produces (ref: src/mesh.cpp:75) -- so the result
+// does not depend on the order in which candidate leaves are tested.
+// NB_SPECULATIVE: a lane that reaches a leaf parks it and keeps walking inner nodes until it finds a second leaf
+// (or every lane of the warp holds one); triangle work then runs with more lanes active.
+#ifndef NB_SPECULATIVE
+#define NB_SPECULATIVE 1
+#endif
+
+template <bool COUNT>
+__device__ __forceinline__ bool leaf_test(const SceneDev &sc, int leaf, Ray &r, Trav &t, bool any_hit, unsigned &n_tris) {
+    const unsigned payload = ~(unsigned) leaf;
+    const unsigned first = payload >> 3, count = (payload & 7u) + 1u;
+    const V3 o = mk(r.ox, r.oy, r.oz), d = mk(r.dx, r.dy, r.dz);
+    for (unsigned i = 0; i < count; ++i) {
+        const float4 a = __ldg(&sc.tris[(size_t) (first + i) * 3 + 0]);
+        const float4 b = __ldg(&sc.tris[(size_t) (first + i) * 3 + 1]);
+        const float4 c = __ldg(&sc.tris[(size_t) (first + i) * 3 + 2]);
+        if (COUNT) n_tris++;
+        // Moeller-Trumbore, operation for operation as ref: src/mesh.cpp:39-76
+        const V3 p0 = xyz(a);
+        const V3 edge1 = xyz(b) - p0, edge2 = xyz(c) - p0;
+        const V3 pvec = cross(d, edge2);
+        const float det = dot(edge1, pvec);
+        if (det > -1e-8f && det < 1e-8f) continue;
+        const float inv_det = 1.0f / det;
+        const V3 tvec = o - p0;
+        const float u = dot(tvec, pvec) * inv_det;
+        if (u < 0.0f || u > 1.0f) continue;
+        const V3 qvec = cross(tvec, edge1);
+        const float v = dot(d, qvec) * inv_det;
+        if (v < 0.0f || u + v > 1.0f) continue;
+        const float tt = dot(edge2, qvec) * inv_det;
+        if (!(tt >= r.mint && tt <= r.maxt)) continue;
+        const uint32_t prim = __float_as_uint(a.w);
+        if (any_hit) { t.hprim = prim; return true; }
+        if (t.hprim == 0xffffffffu || tt < r.maxt || prim > t.hprim) { r.maxt = tt; t.hu = u; t.hv = v; t.hprim = prim; }
+    }
+    return false;
+}
+
 template <bool COUNT, bool TMA_TOP>
-__device__ __forceinline__ bool trav_steps(const SceneDev &sc, const float4 *snodes, int smem_nodes, Ray &r, Trav &t,
-                                           int *stack, bool any_hit, int budget,
-                                           unsigned &n_nodes, unsigned &n_tris) {
+__device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snodes, int smem_nodes, Ray &r, Trav &t,
+                                         int *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris) {
     int node = t.node, sp = t.sp;
-    while (node != kDone) {
+    int parked = 0;                  // postponed leaf ref (leaf refs are negative; 0 = none)
+    while (node != kDone || parked != 0) {
         // ---- inner nodes
         while (node >= 0 && node != kDone) {
-            if (budget-- <= 0) { t.node = node; t.sp = sp; return false; }
             const float4 n0 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 0);
             const float4 n1 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 1);
             const float4 n2 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 2);
@@ -138,44 +175,25 @@ __device__ __forceinline__ bool trav_steps(const SceneDev &sc, const float4 *sno
             } else {
                 node = sp ? stack[--sp] : kDone;
             }
+#if NB_SPECULATIVE
+            if (node < 0 && parked == 0) { parked = node; node = sp ? stack[--sp] : kDone; }
+            if (__ballot_sync(__activemask(), parked == 0) == 0u) break;      // every lane still walking holds a leaf
+#endif
         }
+        // ---- leaves
+#if NB_SPECULATIVE
+        if (parked != 0) {
+            if (leaf_test<COUNT>(sc, parked, r, t, any_hit, n_tris)) break;
+            parked = 0;
+        }
+        if (node < 0) { parked = node; node = sp ? stack[--sp] : kDone; }
+#else
         if (node == kDone) break;
-        // ---- leaf
-        {
-            const unsigned payload = ~(unsigned) node;
-            const unsigned first = payload >> 3, count = (payload & 7u) + 1u;
-            const V3 o = mk(r.ox, r.oy, r.oz), d = mk(r.dx, r.dy, r.dz);
-            for (unsigned i = 0; i < count; ++i) {
-                const float4 a = __ldg(&sc.tris[(size_t) (first + i) * 3 + 0]);
-                const float4 b = __ldg(&sc.tris[(size_t) (first + i) * 3 + 1]);
-                const float4 c = __ldg(&sc.tris[(size_t) (first + i) * 3 + 2]);
-                if (COUNT) n_tris++;
-                // Moeller-Trumbore, operation for operation as ref: src/mesh.cpp:39-76
-                const V3 p0 = xyz(a);
-                const V3 edge1 = xyz(b) - p0, edge2 = xyz(c) - p0;
-                const V3 pvec = cross(d, edge2);
-                const float det = dot(edge1, pvec);
-                if (det > -1e-8f && det < 1e-8f) continue;
-                const float inv_det = 1.0f / det;
-                const V3 tvec = o - p0;
-                const float u = dot(tvec, pvec) * inv_det;
-                if (u < 0.0f || u > 1.0f) continue;
-                const V3 qvec = cross(tvec, edge1);
-                const float v = dot(d, qvec) * inv_det;
-                if (v < 0.0f || u + v > 1.0f) continue;
-                const float tt = dot(edge2, qvec) * inv_det;
-                if (!(tt >= r.mint && tt <= r.maxt)) continue;
-                const uint32_t prim = __float_as_uint(a.w);
-                if (any_hit) { t.hprim = prim; t.node = kDone; t.sp = 0; return true; }
-                if (t.hprim == 0xffffffffu || tt < r.maxt || prim > t.hprim) {
-                    r.maxt = tt; t.hu = u; t.hv = v; t.hprim = prim;
-                }
-            }
-        }
+        if (leaf_test<COUNT>(sc, node, r, t, any_hit, n_tris)) break;
         node = sp ? stack[--sp] : kDone;
+#endif
     }
     t.node = kDone; t.sp = 0;
-    return true;
 }
 
 // ------------------------------------------------------------------ K3: intersection record (ref: src/accel.cpp:45-96)
@@ -484,67 +502,62 @@ __global__ void __launch_bounds__(128, NB_MIN_BLOCKS) render_kernel(const __grid
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
 
     for (;;) {
-        const bool traversing = (ps.stage != ST_IDLE) && (tr.node != kDone);
-        const unsigned busy = __ballot_sync(0xffffffffu, traversing);
-        const unsigned waiting = ~busy;
-        if (__popc(waiting) >= P.refill_threshold || busy == 0u) {
-            // ---- shading phase: lanes whose ray is finished advance their path
-            if (ps.stage != ST_IDLE && tr.node == kDone) {
-                const bool finished = shade<INTEG>(P, ps, ray, tr, n_hits);
-                if (finished) {
-                    splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
-                    ps.stage = ST_IDLE;
-                } else {
-                    trav_begin(ray, tr); n_rays++;
-                }
+        // ---- shading phase (lock step: every lane's ray is finished here)
+        if (ps.stage != ST_IDLE) {
+            const bool finished = shade<INTEG>(P, ps, ray, tr, n_hits);
+            if (finished) {
+                splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
+                ps.stage = ST_IDLE;
+            } else {
+                trav_begin(ray, tr); n_rays++;
             }
-            // ---- regeneration: free lanes take the next items of the warp's unit (ballot/popc compaction)
-            bool need = (ps.stage == ST_IDLE);
-            unsigned need_mask = __ballot_sync(0xffffffffu, need);
-            while (need_mask != 0u && !exhausted) {
-                if (next_item >= n_items) {
-                    unsigned long long u = 0;
-                    if (lane == 0) u = atomicAdd(&P.counters[0], 1ULL);
-                    u = __shfl_sync(0xffffffffu, u, 0);
-                    if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
-                    // unit -> (owned tile, 8x4 patch, sample chunk); patches vary fastest
-                    const uint32_t patch = (uint32_t) (u % 32ULL);
-                    const uint32_t rest = (uint32_t) (u / 32ULL);
-                    const uint32_t chunk_id = rest % P.nchunks;
-                    u_tile_slot = (int) (rest / P.nchunks);
-                    const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;
-                    const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
-                    u_tox = bx * 32; u_toy = by * 32;
-                    u_tsx = min(32, P.W - u_tox); u_tsy = min(32, P.H - u_toy);
-                    u_px0 = u_tox + (int) (patch & 3u) * 8; u_py0 = u_toy + (int) (patch >> 2) * 4;
-                    const int lx = u_px0 + (int) (lane & 7u), ly = u_py0 + (int) (lane >> 3);
-                    valid_mask = __ballot_sync(0xffffffffu, lx < P.W && ly < P.H);
-                    n_valid = __popc(valid_mask);
-                    sample_base = chunk_id * P.chunk;
-                    const uint32_t ns = min(P.chunk, P.spp - sample_base);
-                    n_items = n_valid * ns; next_item = 0;
-                    continue;
-                }
-                const uint32_t avail = n_items - next_item;
-                const uint32_t rank = __popc(need_mask & lt_mask);
-                if (need && rank < avail) {
-                    const uint32_t item = next_item + rank;
-                    const uint32_t pix_slot = item % n_valid, s = sample_base + item / n_valid;
-                    const int pl = __fns(valid_mask, 0, pix_slot + 1);      // lane index of the pix_slot-th valid pixel
-                    ps.tile_slot = u_tile_slot; ps.tox = (short) u_tox; ps.toy = (short) u_toy;
-                    ps.tsx = (unsigned char) u_tsx; ps.tsy = (unsigned char) u_tsy;
-                    begin_path(P, ps, ray, u_px0 + (pl & 7), u_py0 + (pl >> 3), s);
-                    trav_begin(ray, tr); n_rays++;
-                    need = false;
-                }
-                next_item += min((uint32_t) __popc(need_mask), avail);
-                need_mask = __ballot_sync(0xffffffffu, need);
-            }
-            if (exhausted && __ballot_sync(0xffffffffu, ps.stage != ST_IDLE) == 0u) break;
         }
-        // ---- traversal phase
-        if (ps.stage != ST_IDLE && tr.node != kDone)
-            trav_steps<COUNT, TMA_TOP>(P.sc, snodes, smem_nodes, ray, tr, stack, ps.stage != ST_EXTEND, P.step_budget, n_nodes, n_tris);
+        // ---- regeneration: free lanes take the next items of the warp's unit (ballot/popc compaction)
+        bool need = (ps.stage == ST_IDLE);
+        unsigned need_mask = __ballot_sync(0xffffffffu, need);
+        while (need_mask != 0u && !exhausted) {
+            if (next_item >= n_items) {
+                unsigned long long u = 0;
+                if (lane == 0) u = atomicAdd(&P.counters[0], 1ULL);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
+                // unit -> (owned tile, 8x4 patch, sample chunk); patches vary fastest
+                const uint32_t patch = (uint32_t) (u % 32ULL);
+                const uint32_t rest = (uint32_t) (u / 32ULL);
+                const uint32_t chunk_id = rest % P.nchunks;
+                u_tile_slot = (int) (rest / P.nchunks);
+                const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;
+                const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
+                u_tox = bx * 32; u_toy = by * 32;
+                u_tsx = min(32, P.W - u_tox); u_tsy = min(32, P.H - u_toy);
+                u_px0 = u_tox + (int) (patch & 3u) * 8; u_py0 = u_toy + (int) (patch >> 2) * 4;
+                const int lx = u_px0 + (int) (lane & 7u), ly = u_py0 + (int) (lane >> 3);
+                valid_mask = __ballot_sync(0xffffffffu, lx < P.W && ly < P.H);
+                n_valid = __popc(valid_mask);
+                sample_base = chunk_id * P.chunk;
+                const uint32_t ns = min(P.chunk, P.spp - sample_base);
+                n_items = n_valid * ns; next_item = 0;
+                continue;
+            }
+            const uint32_t avail = n_items - next_item;
+            const uint32_t rank = __popc(need_mask & lt_mask);
+            if (need && rank < avail) {
+                const uint32_t item = next_item + rank;
+                const uint32_t pix_slot = item % n_valid, s = sample_base + item / n_valid;
+                const int pl = __fns(valid_mask, 0, pix_slot + 1);      // lane index of the pix_slot-th valid pixel
+                ps.tile_slot = u_tile_slot; ps.tox = (short) u_tox; ps.toy = (short) u_toy;
+                ps.tsx = (unsigned char) u_tsx; ps.tsy = (unsigned char) u_tsy;
+                begin_path(P, ps, ray, u_px0 + (pl & 7), u_py0 + (pl >> 3), s);
+                trav_begin(ray, tr); n_rays++;
+                need = false;
+            }
+            next_item += min((uint32_t) __popc(need_mask), avail);
+            need_mask = __ballot_sync(0xffffffffu, need);
+        }
+        if (__ballot_sync(0xffffffffu, ps.stage != ST_IDLE) == 0u) break;     // work exhausted and every path retired
+        // ---- traversal phase: every active lane walks its ray to completion
+        if (ps.stage != ST_IDLE)
+            trav_run<COUNT, TMA_TOP>(P.sc, snodes, smem_nodes, ray, tr, stack, ps.stage != ST_EXTEND, n_nodes, n_tris);
     }
 
     // counters: warp-reduce then one atomic per warp
@@ -579,7 +592,7 @@ __global__ void __launch_bounds__(32) render_block_mode_kernel(const __grid_cons
         begin_path(P, ps, ray, tox + x, toy + y, i);
         for (;;) {
             trav_begin(ray, tr); n_rays++;
-            while (!trav_steps<COUNT, false>(P.sc, nullptr, 0, ray, tr, stack, ps.stage != ST_EXTEND, 1 << 30, n_nodes, n_tris)) { }
+            trav_run<COUNT, false>(P.sc, nullptr, 0, ray, tr, stack, ps.stage != ST_EXTEND, n_nodes, n_tris);
             if (shade<INTEG>(P, ps, ray, tr, n_hits)) break;
         }
         splat(P, slot, tox, toy, tsx, tsy, ps.sx, ps.sy, ps.L);
@@ -621,7 +634,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(SceneDev sc, const float
         const float4 a = __ldg(&rays[2 * i]), b = __ldg(&rays[2 * i + 1]);
         Ray r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.mint = a.w; r.dx = b.x; r.dy = b.y; r.dz = b.z; r.maxt = b.w;
         Trav t; trav_begin(r, t); n_rays++;
-        while (!trav_steps<COUNT, false>(sc, nullptr, 0, r, t, stack, shadow != 0, 1 << 30, n_nodes, n_tris)) { }
+        trav_run<COUNT, false>(sc, nullptr, 0, r, t, stack, shadow != 0, n_nodes, n_tris);
         if (hits) {
             HitOut h;
             if (t.hprim != 0xffffffffu && !shadow) { h.t = r.maxt; h.u = t.hu; h.v = t.hv; h.prim = t.hprim; h.mesh = __ldg(&sc.faces[t.hprim]).w; }

@@ -194,7 +194,7 @@ def test_instrumented_counts_match_plain(ctx):
     assert sa.rays == sb.rays and sb.node_visits > 0 and sb.tri_tests > 0 and S.rel_l2(a, b) < 1e-6
 
 
-@pytest.mark.parametrize("opt,val", [("smem_nodes", 512), ("refill_threshold", 1), ("refill_threshold", 12), ("chunk", 1), ("chunk", 64), ("blocks_per_sm", 1)])
+@pytest.mark.parametrize("opt,val", [("smem_nodes", 512), ("chunk", 1), ("chunk", 64), ("blocks_per_sm", 1)])
 def test_tuning_options_do_not_change_results(ctx, oracle, opt, val):
     sc = small_ajax(S.INT_AO, 4)
     ctx.load(sc)
@@ -203,7 +203,7 @@ def test_tuning_options_do_not_change_results(ctx, oracle, opt, val):
     try:
         got, _ = ctx.render()
     finally:
-        ctx.set_option(opt, {"smem_nodes": 0, "refill_threshold": 32, "chunk": 8, "blocks_per_sm": 0}[opt])
+        ctx.set_option(opt, {"smem_nodes": 0, "chunk": 8, "blocks_per_sm": 0}[opt])
     assert S.rel_l2(got, ref) < 1e-6
 
 

@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--width", type=int, default=0); ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0); ap.add_argument("--tris", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--grid", default="blocks_per_sm=0;refill_threshold=32;smem_nodes=0;chunk=4")
+    ap.add_argument("--grid", default="blocks_per_sm=0;smem_nodes=0;chunk=8")
     a = ap.parse_args()
     sc = bench.WORKLOADS[a.workload](a)
     ctx = abi.Context(0)
@@ -26,7 +26,7 @@ def main():
     for part in a.grid.split(";"):
         k, vs = part.split("=")
         axes.append([(k, int(v)) for v in vs.split(",")])
-    defaults = {"blocks_per_sm": 0, "refill_threshold": 32, "smem_nodes": 0, "chunk": 4}
+    defaults = {"blocks_per_sm": 0, "smem_nodes": 0, "chunk": 8}
     for combo in itertools.product(*axes):
         rebuild = False
         for k, v in combo:
