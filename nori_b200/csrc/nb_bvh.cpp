@@ -9,6 +9,8 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <thread>
@@ -39,9 +41,23 @@ struct BNode {
     int depth = 0;
 };
 
+// Runs fn(begin, end, chunk) over [b, e) split into `chunks` contiguous pieces on separate threads.
+template <typename F> void parallel_chunks(uint32_t b, uint32_t e, int chunks, F fn) {
+    std::vector<std::thread> th;
+    const uint32_t n = e - b;
+    for (int c = 0; c < chunks; ++c) {
+        const uint32_t cb = b + (uint32_t) ((uint64_t) n * c / chunks), ce = b + (uint32_t) ((uint64_t) n * (c + 1) / chunks);
+        th.emplace_back([=] { fn(cb, ce, c); });
+    }
+    for (auto &t : th) t.join();
+}
+
 struct Builder {
     const PrimRef *prims;
     uint32_t *order;
+    uint32_t *scratch = nullptr;     // same size as order: parallel partition target
+    int nthreads = 1;
+    static constexpr uint32_t kParallelNode = 1u << 19;   // nodes with at least this many triangles are processed by all threads
     std::vector<BNode> nodes;
     std::atomic<uint32_t> nnodes{0};
     std::atomic<int> threads_free{0};
@@ -52,7 +68,18 @@ struct Builder {
     void build(uint32_t ni, uint32_t start, uint32_t end, int depth) {
         Box box, cbox;
         box.reset(); cbox.reset();
-        for (uint32_t i = start; i < end; ++i) { const PrimRef &p = prims[order[i]]; box.grow(p.b); cbox.grow(p.c); }
+        const bool wide = (end - start) >= kParallelNode && nthreads > 1 && threads_free.load(std::memory_order_relaxed) >= nthreads - 1;
+        if (wide) {
+            std::vector<Box> pb((size_t) nthreads), pc((size_t) nthreads);
+            parallel_chunks(start, end, nthreads, [&](uint32_t b, uint32_t e, int c) {
+                Box bb, cc; bb.reset(); cc.reset();
+                for (uint32_t i = b; i < e; ++i) { const PrimRef &p = prims[order[i]]; bb.grow(p.b); cc.grow(p.c); }
+                pb[(size_t) c] = bb; pc[(size_t) c] = cc;
+            });
+            for (int c = 0; c < nthreads; ++c) { box.grow(pb[(size_t) c]); cbox.grow(pc[(size_t) c].lo); cbox.grow(pc[(size_t) c].hi); }
+        } else {
+            for (uint32_t i = start; i < end; ++i) { const PrimRef &p = prims[order[i]]; box.grow(p.b); cbox.grow(p.c); }
+        }
         BNode &nd = nodes[ni];
         nd.box = box; nd.depth = depth;
         const uint32_t n = end - start;
@@ -68,13 +95,28 @@ struct Builder {
                 scale[a] = ext > 0 ? kBins / ext : 0.f;
                 for (int k = 0; k < kBins; ++k) { bins[a][k].reset(); cnt[a][k] = 0; }
             }
-            for (uint32_t i = start; i < end; ++i) {
-                const PrimRef &p = prims[order[i]];
-                for (int a = 0; a < 3; ++a) {
-                    if (scale[a] == 0.f) continue;
-                    int k = std::min(kBins - 1, std::max(0, (int) ((p.c[a] - cbox.lo[a]) * scale[a])));
-                    bins[a][k].grow(p.b); cnt[a][k]++;
+            auto bin_range = [&](uint32_t b, uint32_t e, Box (*bn)[kBins], uint32_t (*cn)[kBins]) {
+                for (uint32_t i = b; i < e; ++i) {
+                    const PrimRef &p = prims[order[i]];
+                    for (int a = 0; a < 3; ++a) {
+                        if (scale[a] == 0.f) continue;
+                        int k = std::min(kBins - 1, std::max(0, (int) ((p.c[a] - cbox.lo[a]) * scale[a])));
+                        bn[a][k].grow(p.b); cn[a][k]++;
+                    }
                 }
+            };
+            if (wide) {
+                struct Part { Box b[3][kBins]; uint32_t c[3][kBins]; };
+                std::vector<Part> parts((size_t) nthreads);
+                parallel_chunks(start, end, nthreads, [&](uint32_t b, uint32_t e, int c) {
+                    Part &pt = parts[(size_t) c];
+                    for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k) { pt.b[a][k].reset(); pt.c[a][k] = 0; }
+                    bin_range(b, e, pt.b, pt.c);
+                });
+                for (auto &pt : parts) for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k)
+                    if (pt.c[a][k]) { bins[a][k].grow(pt.b[a][k]); cnt[a][k] += pt.c[a][k]; }
+            } else {
+                bin_range(start, end, bins, cnt);
             }
             for (int a = 0; a < 3; ++a) {
                 if (scale[a] == 0.f) continue;
@@ -97,12 +139,32 @@ struct Builder {
         } else {
             const int a = best_axis;
             const float sc = kBins / (cbox.hi[a] - cbox.lo[a]), lo = cbox.lo[a];
-            uint32_t *first = order + start, *last = order + end;
-            uint32_t *m = std::partition(first, last, [&](uint32_t id) {
+            auto goes_left = [&](uint32_t id) {
                 int k = std::min(kBins - 1, std::max(0, (int) ((prims[id].c[a] - lo) * sc)));
                 return k <= best_bin;
-            });
-            mid = (uint32_t) (m - order);
+            };
+            if (wide && scratch) {
+                // two-pass parallel partition through the scratch array (stable within chunks)
+                std::vector<uint32_t> nl((size_t) nthreads, 0), nr((size_t) nthreads, 0);
+                parallel_chunks(start, end, nthreads, [&](uint32_t b, uint32_t e, int c) {
+                    uint32_t l = 0; for (uint32_t i = b; i < e; ++i) l += goes_left(order[i]) ? 1u : 0u;
+                    nl[(size_t) c] = l; nr[(size_t) c] = (e - b) - l;
+                });
+                uint32_t total_l = 0; for (uint32_t v : nl) total_l += v;
+                std::vector<uint32_t> ol((size_t) nthreads), orr((size_t) nthreads);
+                uint32_t accl = start, accr = start + total_l;
+                for (int c = 0; c < nthreads; ++c) { ol[(size_t) c] = accl; orr[(size_t) c] = accr; accl += nl[(size_t) c]; accr += nr[(size_t) c]; }
+                parallel_chunks(start, end, nthreads, [&](uint32_t b, uint32_t e, int c) {
+                    uint32_t l = ol[(size_t) c], r = orr[(size_t) c];
+                    for (uint32_t i = b; i < e; ++i) { const uint32_t id = order[i]; if (goes_left(id)) scratch[l++] = id; else scratch[r++] = id; }
+                });
+                parallel_chunks(start, end, nthreads, [&](uint32_t b, uint32_t e, int) { std::memcpy(order + b, scratch + b, sizeof(uint32_t) * (e - b)); });
+                mid = start + total_l;
+            } else {
+                uint32_t *first = order + start, *last = order + end;
+                uint32_t *m = std::partition(first, last, goes_left);
+                mid = (uint32_t) (m - order);
+            }
             if (mid == start || mid == end) mid = start + n / 2;
         }
         const uint32_t l = alloc(), r = alloc();
@@ -152,11 +214,16 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
     for (int a = 0; a < 3; ++a) { out.scene_lo[a] = n ? scene.lo[a] : 0.f; out.scene_hi[a] = n ? scene.hi[a] : 0.f; }
 
     Builder b;
+    std::vector<uint32_t> scratch(n >= Builder::kParallelNode ? n : 0);
     b.prims = prims.data(); b.order = order.data(); b.max_leaf = max_leaf;
+    b.scratch = scratch.empty() ? nullptr : scratch.data();
     b.nodes.resize(n ? 2 * (size_t) n : 1);
     if (nthreads <= 0) nthreads = (int) std::thread::hardware_concurrency();
+    nthreads = std::max(1, std::min(nthreads, 64));
+    b.nthreads = nthreads;
     b.threads_free = std::max(0, nthreads - 1);
     if (n) { uint32_t root = b.alloc(); b.build(root, 0, n, 0); }
+    if (getenv("NB_BVH_TIMING")) fprintf(stderr, "[bvh] refs+build %.2fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 
     // ---- relayout: inner nodes only; BFS for the first bfs_nodes, DFS below ----
     out.nodes.clear(); out.tris.clear(); out.depth = 0;
@@ -188,7 +255,7 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
         absent(nd, 0); absent(nd, 1);
         // An absent child is a one-triangle leaf holding a degenerate (all-zero) triangle: det == 0, always rejected
         // (ref: src/mesh.cpp:52).  (An inverted box would NOT be culled by a min/max slab test.)
-        int32_t r0, r1;
+        int32_t r0 = 0, r1 = 0;
         if (n) { put_box(nd, 0, b.nodes[0].box); r0 = emit_leaf(b.nodes[0]); }
         const uint32_t dummy = (uint32_t) (out.tris.size() / 12);
         for (int k = 0; k < 12; ++k) out.tris.push_back(0.f);
@@ -224,19 +291,48 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
         }
         out.nnodes = (uint32_t) final_order.size();
         out.nodes.assign((size_t) out.nnodes * 16, 0.f);
-        out.tris.reserve((size_t) n * 12);
+        // leaf triangle offsets in final node order (sequential prefix), then nodes + triangles are written in parallel
+        std::vector<uint32_t> leaf_first((size_t) out.nnodes * 2, 0);
+        uint32_t tri_cursor = 0;
         for (uint32_t fi = 0; fi < out.nnodes; ++fi) {
             const BNode &nd = b.nodes[final_order[fi]];
             out.depth = std::max(out.depth, nd.depth + 2);
-            float *o = out.nodes.data() + (size_t) fi * 16;
             const uint32_t ch[2] = { nd.left, nd.right };
             for (int c = 0; c < 2; ++c) {
                 const BNode &cn = b.nodes[ch[c]];
-                put_box(o, c, cn.box);
-                int32_t ref = cn.count > 0 ? emit_leaf(cn) : final_index[ch[c]];
-                std::memcpy(&o[12 + c], &ref, 4);
+                if (cn.count > 0) { leaf_first[(size_t) fi * 2 + c] = tri_cursor; tri_cursor += cn.count; }
             }
         }
+        out.tris.assign((size_t) tri_cursor * 12, 0.f);
+        auto fill = [&](uint32_t fb, uint32_t fe, int) {
+            for (uint32_t fi = fb; fi < fe; ++fi) {
+                const BNode &nd = b.nodes[final_order[fi]];
+                float *o = out.nodes.data() + (size_t) fi * 16;
+                const uint32_t ch[2] = { nd.left, nd.right };
+                for (int c = 0; c < 2; ++c) {
+                    const BNode &cn = b.nodes[ch[c]];
+                    put_box(o, c, cn.box);
+                    int32_t ref;
+                    if (cn.count > 0) {
+                        const uint32_t first = leaf_first[(size_t) fi * 2 + c];
+                        for (uint32_t i = 0; i < cn.count; ++i) {
+                            const uint32_t prim = order[cn.start + i];
+                            float *t = out.tris.data() + (size_t) (first + i) * 12;
+                            for (int k = 0; k < 3; ++k) {
+                                const float *v = in.verts + 4 * (size_t) in.faces[4 * (size_t) prim + k];
+                                t[4 * k] = v[0]; t[4 * k + 1] = v[1]; t[4 * k + 2] = v[2]; t[4 * k + 3] = k == 0 ? as_float(prim) : 0.f;
+                            }
+                        }
+                        ref = (int32_t) ~((first << 3) | (cn.count - 1));
+                    } else {
+                        ref = final_index[ch[c]];
+                    }
+                    std::memcpy(&o[12 + c], &ref, 4);
+                }
+            }
+        };
+        if (out.nnodes >= 65536 && nthreads > 1) parallel_chunks(0, out.nnodes, nthreads, fill);
+        else fill(0, out.nnodes, 0);
     }
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
