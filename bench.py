@@ -127,11 +127,12 @@ def run_reference(args, rank, world):
     scene.spp = max(1, min(full_spp, args.ref_spp))
     cores = os.cpu_count() or 1
     o = pyoracle.OracleScene(scene)
+    accel = 0 if args.accel == "brute" else 1
     for _ in range(max(1, args.warmup) if args.warmup else 0):
-        o.render(accel=1, nthreads=cores)
+        o.render(accel=accel, nthreads=cores)
     secs, rays, samples = 0.0, 0, 0
     for _ in range(args.steps):
-        _, st = o.render(accel=1, nthreads=cores)
+        _, st = o.render(accel=accel, nthreads=cores)
         secs += st.seconds; rays += st.rays; samples += st.samples
     mrays = rays / secs / 1e6
     line = {
@@ -141,7 +142,7 @@ def run_reference(args, rank, world):
         "msamples_per_sec": samples / secs / 1e6,
         "config": {"workload": f"{scene.name} (Ajax stand-in mesh, {scene.n_tris} tris)", "width": scene.camera.width,
                    "height": scene.camera.height, "spp": full_spp, "integrator": "ao" if scene.integrator == 1 else scene.integrator},
-        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "accel": args.accel,
                          "sample": f"full {scene.camera.width}x{scene.camera.height} frame at {scene.spp} of {full_spp} spp per step (Mrays/s is spp-independent)"},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -160,6 +161,8 @@ def main():
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--tris", type=int, default=0)
     ap.add_argument("--ref-spp", type=int, default=32, help="spp per step of the CPU arm (bounded sample)")
+    ap.add_argument("--accel", default="bvh", choices=["bvh", "brute"],
+                    help="CPU arm only: 'brute' = the reference's shipped brute-force Accel (ref: src/accel.cpp:30-43), feasible on --workload bunny")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="key=value tuning option (nb_set_option)")
     args = ap.parse_args()
@@ -208,8 +211,7 @@ def main():
         gathered = MG.gather_blocks(blocks, world, rank, dst=0)      # ONE exchange per frame (NCCL send/recv over NVLink)
         if rank == 0:
             film.zero_()
-            for r in range(world):
-                ctx.merge_blocks_device(gathered[r].data_ptr(), r, world, film.data_ptr(), stream)
+            ctx.merge_all_blocks_device(MG.gathered_base(gathered).data_ptr(), world, n_max, film.data_ptr(), stream)   # one launch
         return st
 
     def barrier():

@@ -139,6 +139,10 @@ int nb_tile_count(nb_ctx *, int rank, int nranks, int *ntiles, int *block_edge);
  * (ref: src/block.cpp:93-102).  film_dev must be zeroed by the caller before the first merge. */
 int nb_merge_blocks_device(nb_ctx *, const float *blocks_dev, int rank, int nranks, float *film_dev, void *stream);
 
+/* The same merge for the gathered blocks of ALL ranks in one launch: blocks_dev = [nranks][stride_tiles][edge][edge][4]
+ * (every rank padded to stride_tiles blocks, as gathered over NCCL). */
+int nb_merge_all_blocks_device(nb_ctx *, const float *blocks_dev, int nranks, int stride_tiles, float *film_dev, void *stream);
+
 /* Batched Scene::rayIntersect (ref: include/nori/scene.h:63-65,82-85 -> src/accel.cpp:23-43).  HOST buffers.
  * shadow != 0: any-hit query, hits[i].prim = 0 if occluded else NB_MISS. */
 int nb_intersect(nb_ctx *, const nb_ray *rays, uint64_t n, nb_hit *hits, int shadow, nb_stats *stats);

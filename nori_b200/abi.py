@@ -80,6 +80,7 @@ def lib():
         L.nb_render_blocks_device.argtypes = [vp, vp, vp, sp]
         L.nb_tile_count.argtypes = [vp, i, i, C.POINTER(i), C.POINTER(i)]
         L.nb_merge_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
+        L.nb_merge_all_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
         L.nb_intersect.argtypes = [vp, vp, u64, vp, i, sp]
         L.nb_intersect_device.argtypes = [vp, vp, u64, vp, i, vp, sp]
         L.nb_intersect_full.argtypes = [vp, vp, u64, vp]
@@ -206,6 +207,9 @@ class Context:
 
     def merge_blocks_device(self, blocks_ptr: int, rank: int, nranks: int, film_ptr: int, stream: int = 0):
         _check(lib().nb_merge_blocks_device(self.h, C.c_void_p(blocks_ptr), rank, nranks, C.c_void_p(film_ptr), C.c_void_p(stream)))
+
+    def merge_all_blocks_device(self, blocks_ptr: int, nranks: int, stride_tiles: int, film_ptr: int, stream: int = 0):
+        _check(lib().nb_merge_all_blocks_device(self.h, C.c_void_p(blocks_ptr), nranks, stride_tiles, C.c_void_p(film_ptr), C.c_void_p(stream)))
 
     def intersect(self, rays: np.ndarray, shadow=False):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

@@ -450,6 +450,23 @@ int nb_merge_blocks_device(nb_ctx *c, const float *blocks_dev, int rank, int nra
     return merge(c, reinterpret_cast<const float4 *>(blocks_dev), n, rank, nranks, reinterpret_cast<float4 *>(film_dev), s);
 }
 
+int nb_merge_all_blocks_device(nb_ctx *c, const float *blocks_dev, int nranks, int stride_tiles, float *film_dev, void *stream) {
+    if (!c || !blocks_dev || !film_dev) return fail("null argument");
+    if (nranks < 1 || stride_tiles < 0) return fail("invalid arguments");
+    if (ensure_device(c)) return 1;
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
+    int ntx = 0, nty = 0;
+    tiles_for(c, 0, 1, &ntx, &nty);
+    const int edge = NB_BLOCK_SIZE + 2 * c->border;
+    const long long total = (long long) nranks * stride_tiles * edge * edge;
+    if (total == 0) return 0;
+    nb::merge_all_blocks_kernel<<<(int) ((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(blocks_dev), nranks, stride_tiles,
+                                                                           ntx * nty, ntx, c->W, c->H, c->border, edge, reinterpret_cast<float4 *>(film_dev));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int nb_render_device(nb_ctx *c, float *film_dev, void *stream, nb_stats *st) {
     if (!c || !film_dev) return fail("null argument");
     cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;

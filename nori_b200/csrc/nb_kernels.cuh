@@ -621,6 +621,28 @@ __global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank,
     atomicAdd(&film[(size_t) (toy + y) * cols + (tox + x)], v);
 }
 
+// Same merge for the gathered blocks of ALL ranks in one launch: blocks = [nranks][stride_tiles][edge][edge] (ranks
+// padded to stride_tiles); slot k of rank r is tile r + k * nranks.
+__global__ void merge_all_blocks_kernel(const float4 *blocks, int nranks, int stride_tiles, int total_tiles, int ntx, int W, int H,
+                                        int border, int block_edge, float4 *film) {
+    const int per_block = block_edge * block_edge;
+    const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long) nranks * stride_tiles * per_block) return;
+    const int r = (int) (gid % per_block);
+    const int slot_all = (int) (gid / per_block);
+    const int rank = slot_all / stride_tiles, slot = slot_all % stride_tiles;
+    const int tile_id = rank + slot * nranks;
+    if (tile_id >= total_tiles) return;
+    const int y = r / block_edge, x = r % block_edge;
+    const int bx = tile_id % ntx, by = tile_id / ntx;
+    const int tox = bx * 32, toy = by * 32;
+    const int tsx = min(32, W - tox), tsy = min(32, H - toy);
+    if (x >= tsx + 2 * border || y >= tsy + 2 * border) return;
+    const float4 v = blocks[gid];
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
+    atomicAdd(&film[(size_t) (toy + y) * (W + 2 * border) + (tox + x)], v);
+}
+
 // ------------------------------------------------------------------ batched Scene::rayIntersect (ref: include/nori/scene.h:63-85)
 struct HitOut { float t, u, v; uint32_t prim; uint32_t mesh; };
 

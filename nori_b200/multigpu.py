@@ -39,9 +39,17 @@ def gather_blocks(blocks, world: int, rank: int, dst: int = 0):
     import torch.distributed as dist
     if world == 1:
         return [blocks]
-    out = [torch.empty_like(blocks) for _ in range(world)] if rank == dst else None
+    out = None
+    if rank == dst:     # one contiguous [world, n_max, E, E, 4] buffer, so the merge is a single launch
+        big = torch.empty((world,) + tuple(blocks.shape), dtype=blocks.dtype, device=blocks.device)
+        out = [big[r] for r in range(world)]
     dist.gather(blocks, out, dst=dst)
     return out
+
+
+def gathered_base(gathered):
+    """The contiguous [world, n_max, E, E, 4] tensor behind gather_blocks' list (world > 1) or the single tensor."""
+    return gathered[0]._base if getattr(gathered[0], "_base", None) is not None else gathered[0]
 
 
 def merge_blocks_numpy(blocks_per_rank, W: int, H: int, border: int):

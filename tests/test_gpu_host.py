@@ -85,5 +85,10 @@ def test_block_api_shards_merge_to_the_full_frame():
                 per_rank.append(blocks.cpu().numpy())
             stream.synchronize()
         ctx.set_tiles(0, 1)
+        film2 = torch.zeros(sc.film_shape, dtype=torch.float32, device="cuda")
+        allb = torch.from_numpy(np.stack(per_rank)).cuda()
+        ctx.merge_all_blocks_device(allb.data_ptr(), world, allb.shape[1], film2.data_ptr(), 0)
+        torch.cuda.synchronize()
     assert S.rel_l2(film.cpu().numpy(), full) < 1e-6
+    assert S.rel_l2(film2.cpu().numpy(), full) < 1e-6
     assert S.rel_l2(MG.merge_blocks_numpy(per_rank, W, H, b), full) < 1e-6

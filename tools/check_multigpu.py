@@ -27,8 +27,7 @@ ctx.render_blocks_device(blocks.data_ptr(), stream.cuda_stream)
 got = MG.gather_blocks(blocks, world, rank)
 if rank == 0:
     film = torch.zeros(sc.film_shape, dtype=torch.float32, device=dev)
-    for r in range(world):
-        ctx.merge_blocks_device(got[r].data_ptr(), r, world, film.data_ptr(), stream.cuda_stream)
+    ctx.merge_all_blocks_device(MG.gathered_base(got).data_ptr(), world, MG.max_tiles(world, W, H), film.data_ptr(), stream.cuda_stream)
     stream.synchronize()
     ctx.set_tiles(0, 1)
     ref, _ = ctx.render()
