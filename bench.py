@@ -307,7 +307,7 @@ def main():
             "e2e": {"value": tot_rays / (e2e_mean_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_mean_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "nb_upload_scene (scene arrays from pinned host memory) + nb_render into a host film"},
-            "gpu_launches": int(args.steps * 2 * world),
+            "gpu_launches": int(args.steps * (world + 1)),   # per step: one render_kernel per rank + one merge kernel on rank 0
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.workload) if world == 1 else None, "peak_source": peak_src, "kernel": "render_kernel<ao>",
                          "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_launch": alg_bytes / world,

@@ -2,6 +2,7 @@
 #include <fstream>
 #include <sstream>
 #include <unordered_map>
+#include <sys/stat.h>
 #include "nori/parser.h"
 #include "nori/plugins.h"
 
@@ -45,6 +46,11 @@ public:
         std::ifstream is(filename);
         if (is.fail()) throw NoriException("Unable to open OBJ file \"%s\"!", filename);
         Transform trafo = propList.getTransform("toWorld", Transform());
+        m_name = filename;
+        /* binary cache of the parsed arrays next to the OBJ: text parsing through istringstream +
+           hash-map dedup is the slowest load step for 500k-triangle meshes.  Opt in with <boolean name="cache" value="true"/>. */
+        const bool useCache = propList.getBoolean("cache", false);
+        if (useCache && loadCache(filename, trafo)) return;
 
         std::vector<Vector3f> positions, normals;
         std::vector<Point2f> texcoords;
@@ -112,10 +118,52 @@ public:
                 m_UV[2 * i] = texcoords[vertices[i].uv - 1].x; m_UV[2 * i + 1] = texcoords[vertices[i].uv - 1].y;
             }
         }
-        m_name = filename;
+        if (useCache) saveCache(filename, trafo);
     }
 
 protected:
+    struct CacheHeader { char magic[8]; uint64_t objSize; int64_t objMtime; float trafo[16]; uint32_t nv, nf, hasN, hasUV; };
+
+    static bool statFile(const std::string &f, uint64_t &size, int64_t &mtime) {
+        struct stat st;
+        if (stat(f.c_str(), &st) != 0) return false;
+        size = (uint64_t) st.st_size; mtime = (int64_t) st.st_mtime;
+        return true;
+    }
+    void fillHeader(const std::string &filename, const Transform &trafo, CacheHeader &h) const {
+        std::memset(&h, 0, sizeof h);
+        std::memcpy(h.magic, "NBMESH01", 8);
+        statFile(filename, h.objSize, h.objMtime);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) h.trafo[4 * i + j] = trafo.getMatrix()(i, j);
+    }
+    bool loadCache(const std::string &filename, const Transform &trafo) {
+        std::ifstream cs(filename + ".nbcache", std::ios::binary);
+        if (!cs) return false;
+        CacheHeader want, got;
+        fillHeader(filename, trafo, want);
+        cs.read((char *) &got, sizeof got);
+        if (!cs || std::memcmp(got.magic, want.magic, 8) || got.objSize != want.objSize || got.objMtime != want.objMtime ||
+            std::memcmp(got.trafo, want.trafo, sizeof got.trafo)) return false;
+        m_V.resize((size_t) got.nv * 3); m_F.resize((size_t) got.nf * 3);
+        cs.read((char *) m_V.data(), (std::streamsize) (m_V.size() * 4));
+        cs.read((char *) m_F.data(), (std::streamsize) (m_F.size() * 4));
+        if (got.hasN) { m_N.resize((size_t) got.nv * 3); cs.read((char *) m_N.data(), (std::streamsize) (m_N.size() * 4)); }
+        if (got.hasUV) { m_UV.resize((size_t) got.nv * 2); cs.read((char *) m_UV.data(), (std::streamsize) (m_UV.size() * 4)); }
+        if (!cs) { m_V.clear(); m_F.clear(); m_N.clear(); m_UV.clear(); return false; }
+        return true;
+    }
+    void saveCache(const std::string &filename, const Transform &trafo) const {
+        std::ofstream cs(filename + ".nbcache", std::ios::binary);
+        if (!cs) return;   /* read-only scene directory: silently skip */
+        CacheHeader h; fillHeader(filename, trafo, h);
+        h.nv = getVertexCount(); h.nf = getTriangleCount(); h.hasN = !m_N.empty(); h.hasUV = !m_UV.empty();
+        cs.write((const char *) &h, sizeof h);
+        cs.write((const char *) m_V.data(), (std::streamsize) (m_V.size() * 4));
+        cs.write((const char *) m_F.data(), (std::streamsize) (m_F.size() * 4));
+        if (h.hasN) cs.write((const char *) m_N.data(), (std::streamsize) (m_N.size() * 4));
+        if (h.hasUV) cs.write((const char *) m_UV.data(), (std::streamsize) (m_UV.size() * 4));
+    }
+
     struct OBJVertex {   /* ref: src/obj.cpp:122-147 */
         uint32_t p = (uint32_t) -1, n = (uint32_t) -1, uv = (uint32_t) -1;
         OBJVertex() { }

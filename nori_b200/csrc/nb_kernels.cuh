@@ -24,6 +24,16 @@ namespace nb {
 #ifndef NB_MIN_BLOCKS
 #define NB_MIN_BLOCKS 10
 #endif
+// Path integrators (whitted / path_*) carry more live state and heavier shading code; they get their own cap.
+#ifndef NB_MIN_BLOCKS_PATH
+#define NB_MIN_BLOCKS_PATH 10
+#endif
+#ifndef NB_WALK_NOINLINE
+#define NB_WALK_NOINLINE 1
+#endif
+#ifndef NB_SPLAT_HOIST
+#define NB_SPLAT_HOIST 1
+#endif
 constexpr int kStack = 64;          // builder guarantees depth < 64 (nb_bvh.cpp)
 constexpr int kBlockEdgeMax = 32 + 2 * 8;
 
@@ -145,6 +155,9 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
                                          int *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris) {
     int node = t.node, sp = t.sp;
     int parked = 0;                  // postponed leaf ref (leaf refs are negative; 0 = none)
+#if NB_SPECULATIVE >= 2
+    int parked2 = 0;
+#endif
     while (node != kDone || parked != 0) {
         // ---- inner nodes
         while (node >= 0 && node != kDone) {
@@ -177,7 +190,12 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
             }
 #if NB_SPECULATIVE
             if (node < 0 && parked == 0) { parked = node; node = sp ? stack[--sp] : kDone; }
+#if NB_SPECULATIVE >= 2
+            if (node < 0 && parked2 == 0) { parked2 = node; node = sp ? stack[--sp] : kDone; }
+            if (__ballot_sync(__activemask(), parked2 == 0) == 0u) break;
+#else
             if (__ballot_sync(__activemask(), parked == 0) == 0u) break;      // every lane still walking holds a leaf
+#endif
 #endif
         }
         // ---- leaves
@@ -186,6 +204,12 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
             if (leaf_test<COUNT>(sc, parked, r, t, any_hit, n_tris)) break;
             parked = 0;
         }
+#if NB_SPECULATIVE >= 2
+        if (parked2 != 0) {
+            if (leaf_test<COUNT>(sc, parked2, r, t, any_hit, n_tris)) break;
+            parked2 = 0;
+        }
+#endif
         if (node < 0) { parked = node; node = sp ? stack[--sp] : kDone; }
 #else
         if (node == kDone) break;
@@ -194,6 +218,30 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
 #endif
     }
     t.node = kDone; t.sp = 0;
+}
+
+// Out-of-line entry to the walk.  The walk is the hot loop; calling it through a real function boundary gives it
+// its own register allocation (the caller's path state is saved around ONE call per ray instead of being spilled
+// inside the loop) and its own traversal stack, independent of which integrator the kernel was instantiated for.
+struct WalkResult { float t, u, v; uint32_t prim; unsigned n_nodes, n_tris; };
+
+#if NB_WALK_NOINLINE
+#define NB_WALK_ATTR __noinline__
+#else
+#define NB_WALK_ATTR __forceinline__
+#endif
+template <bool COUNT, bool TMA_TOP>
+__device__ NB_WALK_ATTR WalkResult walk(const float4 *nodes, const float4 *tris, const float4 *snodes, int smem_nodes,
+                                        float ox, float oy, float oz, float mint, float dx, float dy, float dz, float maxt, bool any_hit) {
+    int stack[kStack];
+    SceneDev sc;
+    sc.nodes = nodes; sc.tris = tris;
+    Ray r; r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.mint = mint; r.maxt = maxt;
+    Trav t; trav_begin(r, t);
+    unsigned nn = 0, nt = 0;
+    trav_run<COUNT, TMA_TOP>(sc, snodes, smem_nodes, r, t, stack, any_hit, nn, nt);
+    WalkResult w; w.t = r.maxt; w.u = t.hu; w.v = t.hv; w.prim = t.hprim; w.n_nodes = nn; w.n_tris = nt;
+    return w;
 }
 
 // ------------------------------------------------------------------ K3: intersection record (ref: src/accel.cpp:45-96)
@@ -259,6 +307,21 @@ __device__ __forceinline__ void splat(const RenderParams &P, int tile_slot, int 
     x0 = max(x0, 0); y0 = max(y0, 0);
     x1 = min(x1, tsx + 2 * bd - 1); y1 = min(y1, tsy + 2 * bd - 1);
     float4 *blk = P.blocks + (size_t) tile_slot * P.block_edge * P.block_edge;
+    const int nx = x1 - x0 + 1;
+    if (NB_SPLAT_HOIST && nx <= 6) {
+        // common case (radius <= 2.5): the column weights are looked up once and kept in registers
+        float wxs[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) wxs[i] = i < nx ? P.ftable[(int) (fabsf((float) (x0 + i) - posx) * P.lookup)] : 0.0f;
+        for (int y = y0; y <= y1; ++y) {
+            const float wy = P.ftable[(int) (fabsf((float) y - posy) * P.lookup)];
+            float4 *row = blk + y * P.block_edge + x0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                if (i < nx) atomicAdd(&row[i], make_float4(value.x * wxs[i] * wy, value.y * wxs[i] * wy, value.z * wxs[i] * wy, 1.0f * wxs[i] * wy));
+        }
+        return;
+    }
     for (int y = y0; y <= y1; ++y) {
         const float wy = P.ftable[(int) (fabsf((float) y - posy) * P.lookup)];
         for (int x = x0; x <= x1; ++x) {
@@ -482,7 +545,7 @@ __device__ __forceinline__ void tma_stage_nodes(float4 *snodes, const float4 *gn
 
 // ------------------------------------------------------------------ the fused persistent kernel (K1..K5)
 template <int INTEG, bool COUNT, bool TMA_TOP>
-__global__ void __launch_bounds__(128, NB_MIN_BLOCKS) render_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLOCKS_PATH) render_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *snodes = reinterpret_cast<float4 *>(smem_raw);
     __shared__ __align__(8) uint64_t mbar;
@@ -491,7 +554,7 @@ __global__ void __launch_bounds__(128, NB_MIN_BLOCKS) render_kernel(const __grid
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int stack[kStack];
+    // (the traversal stack lives inside walk())
     Path ps; Ray ray; Trav tr;
     ps.stage = ST_IDLE; tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu;
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
@@ -509,7 +572,7 @@ __global__ void __launch_bounds__(128, NB_MIN_BLOCKS) render_kernel(const __grid
                 splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
                 ps.stage = ST_IDLE;
             } else {
-                trav_begin(ray, tr); n_rays++;
+                n_rays++;
             }
         }
         // ---- regeneration: free lanes take the next items of the warp's unit (ballot/popc compaction)
@@ -548,7 +611,7 @@ __global__ void __launch_bounds__(128, NB_MIN_BLOCKS) render_kernel(const __grid
                 ps.tile_slot = u_tile_slot; ps.tox = (short) u_tox; ps.toy = (short) u_toy;
                 ps.tsx = (unsigned char) u_tsx; ps.tsy = (unsigned char) u_tsy;
                 begin_path(P, ps, ray, u_px0 + (pl & 7), u_py0 + (pl >> 3), s);
-                trav_begin(ray, tr); n_rays++;
+                n_rays++;
                 need = false;
             }
             next_item += min((uint32_t) __popc(need_mask), avail);
@@ -556,8 +619,12 @@ __global__ void __launch_bounds__(128, NB_MIN_BLOCKS) render_kernel(const __grid
         }
         if (__ballot_sync(0xffffffffu, ps.stage != ST_IDLE) == 0u) break;     // work exhausted and every path retired
         // ---- traversal phase: every active lane walks its ray to completion
-        if (ps.stage != ST_IDLE)
-            trav_run<COUNT, TMA_TOP>(P.sc, snodes, smem_nodes, ray, tr, stack, ps.stage != ST_EXTEND, n_nodes, n_tris);
+        if (ps.stage != ST_IDLE) {
+            const WalkResult w = walk<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray.ox, ray.oy, ray.oz, ray.mint,
+                                                      ray.dx, ray.dy, ray.dz, ray.maxt, ps.stage != ST_EXTEND);
+            ray.maxt = w.t; tr.hu = w.u; tr.hv = w.v; tr.hprim = w.prim;
+            if (COUNT) { n_nodes += w.n_nodes; n_tris += w.n_tris; }
+        }
     }
 
     // counters: warp-reduce then one atomic per warp

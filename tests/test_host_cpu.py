@@ -110,3 +110,23 @@ def test_block_generator_spiral_matches_oracle(oracle):
         assert np.all(hb[:, 2] == np.minimum(32, W - hb[:, 0])) and np.all(hb[:, 3] == np.minimum(32, H - hb[:, 1]))
         assert len({(int(a), int(b)) for a, b in hb[:, :2]}) == n
     assert host.block_order(768, 768)[0, :2].tolist() == [384, 384]        # starts at the centre block
+
+
+def test_obj_binary_cache_round_trip(tmp_path):
+    """Opt-in mesh cache: second load comes from <obj>.nbcache and yields identical arrays; the cache
+    is invalidated when the OBJ or the toWorld transform changes."""
+    m = S.golden_mesh("cbox_sphere1")
+    S.write_obj(str(tmp_path / "s.obj"), m)
+    xml = """<scene><integrator type="normals"/><camera type="perspective"/>
+      <mesh type="obj"><string name="filename" value="s.obj"/><boolean name="cache" value="true"/>%s</mesh></scene>"""
+    (tmp_path / "a.xml").write_text(xml % "")
+    a = host.HostScene(str(tmp_path / "a.xml")).mesh(0)
+    assert (tmp_path / "s.obj.nbcache").exists()
+    b = host.HostScene(str(tmp_path / "a.xml")).mesh(0)          # served by the cache
+    for k in ("V", "F", "N"):
+        assert np.array_equal(a[k], b[k])
+    (tmp_path / "b.xml").write_text(xml % '<transform name="toWorld"><scale value="2,2,2"/></transform>')
+    c = host.HostScene(str(tmp_path / "b.xml")).mesh(0)          # different transform -> cache rejected and rewritten
+    assert np.allclose(c["V"], 2 * a["V"], rtol=1e-6)
+    d = host.HostScene(str(tmp_path / "a.xml")).mesh(0)
+    assert np.array_equal(d["V"], a["V"])
