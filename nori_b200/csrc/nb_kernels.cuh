@@ -29,7 +29,7 @@ namespace nb {
 #define NB_MIN_BLOCKS_PATH 10
 #endif
 #ifndef NB_WALK_NOINLINE
-#define NB_WALK_NOINLINE 1
+#define NB_WALK_NOINLINE 0
 #endif
 #ifndef NB_SPLAT_HOIST
 #define NB_SPLAT_HOIST 1
@@ -220,9 +220,9 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
     t.node = kDone; t.sp = 0;
 }
 
-// Out-of-line entry to the walk.  The walk is the hot loop; calling it through a real function boundary gives it
-// its own register allocation (the caller's path state is saved around ONE call per ray instead of being spilled
-// inside the loop) and its own traversal stack, independent of which integrator the kernel was instantiated for.
+// Entry to the walk (one call per ray).  NB_WALK_NOINLINE=1 compiles it as a real function with its own register
+// allocation and traversal stack; measured 4-15 % SLOWER than inlining on B200 (profiles/r1_v6_variant_matrix.txt),
+// so the default inlines it.
 struct WalkResult { float t, u, v; uint32_t prim; unsigned n_nodes, n_tris; };
 
 #if NB_WALK_NOINLINE
