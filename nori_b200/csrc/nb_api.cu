@@ -76,7 +76,7 @@ struct nb_ctx {
     unsigned long long *counters = nullptr;          // 8 x u64 device
     unsigned long long *counters_h = nullptr;        // pinned
     // options
-    int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 8, opt_count = 0, opt_max_leaf = 3,
+    int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 0, opt_count = 0, opt_max_leaf = 3,
             opt_bfs_nodes = 2048;
 };
 
@@ -146,7 +146,15 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     P.n_my_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, &P.ntx, &P.nty);
     P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
     if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
-    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(c->opt_chunk, c->spp));
+    // samples per work unit: explicit option, else as coarse as 8 while leaving >= 16 units per resident warp
+    // (few tiles per GPU at N = 8 would otherwise quantise the tail: 2.6 units per warp at chunk 8)
+    int64_t chunk = c->opt_chunk;
+    if (chunk <= 0) {
+        const int64_t warps = (int64_t) c->sm_count * NB_MIN_BLOCKS * 4;
+        const int64_t units1 = (int64_t) P.n_my_tiles * 32 * c->spp;
+        chunk = std::max<int64_t>(1, std::min<int64_t>(8, units1 / (16 * warps)));
+    }
+    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, c->spp));
     P.nchunks = (c->spp + P.chunk - 1) / P.chunk;
     const unsigned long long units = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
     if (units > 0xffffffffULL) return fail("too many work units");

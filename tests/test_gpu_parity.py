@@ -203,7 +203,7 @@ def test_tuning_options_do_not_change_results(ctx, oracle, opt, val):
     try:
         got, _ = ctx.render()
     finally:
-        ctx.set_option(opt, {"smem_nodes": 0, "chunk": 8, "blocks_per_sm": 0}[opt])
+        ctx.set_option(opt, {"smem_nodes": 0, "chunk": 0, "blocks_per_sm": 0}[opt])
     assert S.rel_l2(got, ref) < 1e-6
 
 

@@ -16,17 +16,20 @@ def main():
     ap.add_argument("--width", type=int, default=0); ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0); ap.add_argument("--tris", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--grid", default="blocks_per_sm=0;smem_nodes=0;chunk=8")
+    ap.add_argument("--tiles", default="0,1", help="rank,nranks tile shard to emulate one rank of an N-GPU run")
+    ap.add_argument("--grid", default="blocks_per_sm=0;smem_nodes=0;chunk=0")
     a = ap.parse_args()
     sc = bench.WORKLOADS[a.workload](a)
     ctx = abi.Context(0)
     ctx.load(sc)
-    print(json.dumps({"scene": sc.name, **ctx.scene_info()}))
+    r, n = (int(v) for v in a.tiles.split(","))
+    ctx.set_tiles(r, n)
+    print(json.dumps({"scene": sc.name, "tiles": a.tiles, **ctx.scene_info()}))
     axes = []
     for part in a.grid.split(";"):
         k, vs = part.split("=")
         axes.append([(k, int(v)) for v in vs.split(",")])
-    defaults = {"blocks_per_sm": 0, "smem_nodes": 0, "chunk": 8}
+    defaults = {"blocks_per_sm": 0, "smem_nodes": 0, "chunk": 0}
     for combo in itertools.product(*axes):
         rebuild = False
         for k, v in combo:
