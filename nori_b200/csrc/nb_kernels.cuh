@@ -26,7 +26,10 @@ namespace nb {
 #endif
 // Path integrators (whitted / path_*) carry more live state and heavier shading code; they get their own cap.
 #ifndef NB_MIN_BLOCKS_PATH
-#define NB_MIN_BLOCKS_PATH 10
+#define NB_MIN_BLOCKS_PATH 11
+#endif
+#ifndef NB_SPEC_VOTE
+#define NB_SPEC_VOTE 1
 #endif
 #ifndef NB_WALK_NOINLINE
 #define NB_WALK_NOINLINE 0
@@ -193,7 +196,7 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
 #if NB_SPECULATIVE >= 2
             if (node < 0 && parked2 == 0) { parked2 = node; node = sp ? stack[--sp] : kDone; }
             if (__ballot_sync(__activemask(), parked2 == 0) == 0u) break;
-#else
+#elif NB_SPEC_VOTE
             if (__ballot_sync(__activemask(), parked == 0) == 0u) break;      // every lane still walking holds a leaf
 #endif
 #endif
