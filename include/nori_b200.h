@@ -156,6 +156,9 @@ int nb_film_to_rgb(nb_ctx *, const float *film_host, float *rgb_host);
 
 /* Tuning knobs (optional; sane defaults): key/value, see DESIGN.md section 6.  Unknown key -> error. */
 int nb_set_option(nb_ctx *, const char *key, int64_t value);
+/* Raw device counters of the last call (diagnostics; meaningful with option "count" = 1): [1] rays, [2] node visits,
+ * [3] triangle tests, [4] hits shaded, [5] sum over lock-step waves of the LONGEST walk in the warp, [6] waves. */
+int nb_debug_counters(nb_ctx *, uint64_t out[8]);
 /* Scene geometry summary after nb_build_accel. */
 int nb_scene_info(nb_ctx *, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_bytes, int *bvh_depth);
 

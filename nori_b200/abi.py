@@ -86,6 +86,7 @@ def lib():
         L.nb_intersect_full.argtypes = [vp, vp, u64, vp]
         L.nb_film_to_rgb.argtypes = [vp, vp, vp]
         L.nb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.nb_debug_counters.argtypes = [vp, vp]
         L.nb_scene_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i)]
         _lib = L
     return _lib
@@ -175,6 +176,11 @@ class Context:
         n, e = C.c_int(), C.c_int()
         _check(lib().nb_tile_count(self.h, rank, nranks, C.byref(n), C.byref(e)))
         return n.value, e.value
+
+    def debug_counters(self):
+        out = np.zeros(8, dtype=np.uint64)
+        _check(lib().nb_debug_counters(self.h, _p(out)))
+        return out
 
     def scene_info(self):
         a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()

@@ -596,6 +596,12 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     return 0;
 }
 
+int nb_debug_counters(nb_ctx *c, uint64_t out[8]) {
+    if (!c || !out) return fail("null argument");
+    for (int i = 0; i < 8; ++i) out[i] = c->counters_h[i];
+    return 0;
+}
+
 int nb_scene_info(nb_ctx *c, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_bytes, int *bvh_depth) {
     if (!c) return fail("null context");
     if (!c->built) return fail("nb_build_accel has not been called");

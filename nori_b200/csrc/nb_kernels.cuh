@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
     Path ps; Ray ray; Trav tr;
     ps.stage = ST_IDLE; tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu;
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
+    unsigned wave_nodes = 0; unsigned long long wave_max_sum = 0, n_waves = 0;
 
     // warp-uniform work-unit state
     bool exhausted = false;
@@ -626,7 +627,14 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
             const WalkResult w = walk<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray.ox, ray.oy, ray.oz, ray.mint,
                                                       ray.dx, ray.dy, ray.dz, ray.maxt, ps.stage != ST_EXTEND);
             ray.maxt = w.t; tr.hu = w.u; tr.hv = w.v; tr.hprim = w.prim;
-            if (COUNT) { n_nodes += w.n_nodes; n_tris += w.n_tris; }
+            if (COUNT) { n_nodes += w.n_nodes; n_tris += w.n_tris; wave_nodes = w.n_nodes; }
+        }
+        if (COUNT) {
+            // lock-step diagnostics: per wave, the longest walk (what the warp pays) vs the sum over lanes (what it needs)
+            unsigned mx = wave_nodes;
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) { wave_max_sum += mx; n_waves++; }
+            wave_nodes = 0;
         }
     }
 
@@ -638,7 +646,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
     }
     if (lane == 0) {
         atomicAdd(&P.counters[1], v1);
-        if (COUNT) { atomicAdd(&P.counters[2], v2); atomicAdd(&P.counters[3], v3); }
+        if (COUNT) { atomicAdd(&P.counters[2], v2); atomicAdd(&P.counters[3], v3); atomicAdd(&P.counters[5], wave_max_sum); atomicAdd(&P.counters[6], n_waves); }
         atomicAdd(&P.counters[4], v4);
     }
 }
