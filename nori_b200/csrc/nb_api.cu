@@ -171,7 +171,10 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     }
     P.blocks = blocks_out;
     P.counters = c->counters;
-    const bool block_mode = c->seed_mode == NB_SEED_PER_BLOCK;
+    // Reference per-block streams are sequential by construction; only `normals` consumes a fixed number of draws per
+    // sample (4), which lets the parallel kernel jump to each sample's stream position (pcg32 skip-ahead).
+    P.block_stream_skip = (c->seed_mode == NB_SEED_PER_BLOCK && c->integ.type == NB_INT_NORMALS) ? 1 : 0;
+    const bool block_mode = c->seed_mode == NB_SEED_PER_BLOCK && !P.block_stream_skip;
     const bool count = c->opt_count != 0;
     P.smem_nodes = (block_mode || count) ? 0 : (int) std::min<int64_t>(std::min<int64_t>(c->opt_smem_nodes, c->top_nodes), 3400);
     const size_t smem = (size_t) P.smem_nodes * 64;

@@ -47,6 +47,17 @@ __device__ __forceinline__ void pcg_seed(Pcg32 &r, uint64_t initstate, uint64_t 
     r.state = 0u; r.inc = (initseq << 1u) | 1u;
     pcg_next_uint(r); r.state += initstate; pcg_next_uint(r);
 }
+// pcg32::advance -- O(log delta) skip-ahead of the LCG (Brown, "Random Number Generation with Arbitrary Strides")
+__device__ __forceinline__ void pcg_advance(Pcg32 &r, uint64_t delta) {
+    uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = r.inc, acc_mult = 1u, acc_plus = 0u;
+    while (delta > 0) {
+        if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    r.state = acc_mult * r.state + acc_plus;
+}
 __device__ __forceinline__ float pcg_next_float(Pcg32 &r) {
     return __uint_as_float((pcg_next_uint(r) >> 9) | 0x3f800000u) - 1.0f;
 }

@@ -76,6 +76,7 @@ struct RenderParams {
     float4 *blocks;                 // n_my_tiles x block_edge x block_edge
     unsigned long long *counters;   // [0] next unit, [1] rays, [2] node visits, [3] tri tests, [4] hits shaded
     int32_t smem_nodes;             // nodes staged in shared memory (0 = none)
+    int32_t block_stream_skip;      // per-block seeding served by skip-ahead (fixed draws per sample)
 };
 
 // ------------------------------------------------------------------ traversal state (per lane)
@@ -513,6 +514,14 @@ __device__ __forceinline__ void begin_path(const RenderParams &P, Path &ps, Ray 
     if (P.seed_mode == 0) {
         const uint64_t pix = (uint64_t) py * (uint64_t) P.W + (uint64_t) px;
         pcg_seed(ps.rng, (P.seed << 32) + pix, (uint64_t) sample);
+    } else if (P.block_stream_skip) {
+        // reference per-block stream (ref: src/independent.cpp:36-41) for integrators with a FIXED number of draws per
+        // sample (normals: the 4 camera draws): sample j of the block sits at stream position 4*j, reached by skip-ahead
+        const int tox = (px / 32) * 32, toy = (py / 32) * 32;
+        const int tsx = min(32, P.W - tox);
+        const uint64_t j = ((uint64_t) (py - toy) * (uint64_t) tsx + (uint64_t) (px - tox)) * (uint64_t) P.spp + (uint64_t) sample;
+        pcg_seed(ps.rng, (uint64_t) tox, (uint64_t) toy);
+        pcg_advance(ps.rng, 4ull * j);
     }
     ps.sx = (float) px + pcg_next_float(ps.rng);
     ps.sy = (float) py + pcg_next_float(ps.rng);

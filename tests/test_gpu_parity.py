@@ -130,6 +130,16 @@ def test_film_parity_reference_block_seeding(ctx, oracle):
     _film_parity(ctx, oracle, S.config_bunny())
 
 
+def test_film_parity_block_seeding_sequential_integrators(ctx, oracle):
+    """Per-block streams with data-dependent draw counts (ao, path_mis) run one device thread per block."""
+    for sc in (small_ajax(S.INT_AO, 2, 100, 70), S.config_cbox(64, 48, 2, S.INT_PATH_MIS)):
+        sc.seed_mode = S.SEED_PER_BLOCK
+        _film_parity(ctx, oracle, sc)
+    sc = small_ajax(S.INT_NORMALS, 3, 100, 70)     # ragged tiles + several spp through the skip-ahead path
+    sc.seed_mode = S.SEED_PER_BLOCK
+    _film_parity(ctx, oracle, sc)
+
+
 def test_film_parity_ao(ctx, oracle):
     _film_parity(ctx, oracle, small_ajax(S.INT_AO, 8))
 
