@@ -97,6 +97,10 @@ int nb_clear_meshes(nb_ctx *);
 /* Replaces Accel::build (ref: src/accel.cpp:19-21; called from Scene::activate, ref: src/scene.cpp:28):
  * host SAH BVH build + SoA upload. */
 int nb_build_accel(nb_ctx *);
+/* Seconds the last nb_build_accel spent building the hierarchy and which builder ran: 0 = host binned SAH (default),
+ * 1 = device LBVH (nb_set_option(ctx, "builder", 1); Morton sort + Karras radix tree on the GPU, ~100x faster to
+ * build, lower tree quality).  Results are identical with either tree. */
+int nb_build_stats(nb_ctx *, double *seconds, int *builder);
 /* Re-uploads the already built scene arrays from pinned host memory (used to time host->device traffic). */
 int nb_upload_scene(nb_ctx *);
 

@@ -70,6 +70,7 @@ def lib():
         L.nb_clear_meshes.argtypes = [vp]
         L.nb_build_accel.argtypes = [vp]
         L.nb_upload_scene.argtypes = [vp]
+        L.nb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i)]
         L.nb_set_camera.argtypes = [vp, vp, vp, i, i, f, f]
         L.nb_set_filter.argtypes = [vp, vp, f]
         L.nb_set_sampler.argtypes = [vp, u32, i, u64]
@@ -165,6 +166,11 @@ class Context:
         _check(L.nb_set_sampler(self.h, scene.spp, scene.seed_mode, scene.seed))
         it = IntegratorDesc(int(scene.integrator), int(scene.rr_start), int(scene.max_depth), 0)
         _check(L.nb_set_integrator(self.h, C.byref(it)))
+
+    def build_stats(self):
+        sec, b = C.c_double(), C.c_int()
+        _check(lib().nb_build_stats(self.h, C.byref(sec), C.byref(b)))
+        return dict(seconds=sec.value, builder="device-lbvh" if b.value == 1 else "host-sah")
 
     def upload(self):
         _check(lib().nb_upload_scene(self.h))

@@ -5,6 +5,7 @@
 #include "../../include/nori_b200.h"
 #include "nb_bvh.h"
 #include "nb_kernels.cuh"
+#include "nb_lbvh.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -77,7 +78,8 @@ struct nb_ctx {
     unsigned long long *counters_h = nullptr;        // pinned
     // options
     int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 0, opt_count = 0, opt_max_leaf = 3,
-            opt_bfs_nodes = 2048;
+            opt_bfs_nodes = 2048, opt_builder = 0;
+    int builder_used = 0;   // 0 host SAH, 1 device LBVH
 };
 
 namespace {
@@ -248,6 +250,59 @@ int finish_stats(nb_ctx *c, cudaStream_t s, nb_stats *st, int extra_launches) {
     return 0;
 }
 
+// Device LBVH build (nb_lbvh.cuh).  verts / faces must already be on the device.  Fills c->nodes / c->tris (device + pinned
+// mirrors) and the node count.
+int build_lbvh_device(nb_ctx *c, size_t nf, float pad, const float clo[3], const float chi[3]) {
+    const int n = (int) nf;
+    cudaStream_t s = c->stream;
+    nb::LbvhScratch L;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(L.keys); cudaFree(L.keys_sorted); cudaFree(L.leaf_lo); cudaFree(L.leaf_hi); cudaFree(L.node_lo); cudaFree(L.node_hi);
+        cudaFree(L.children); cudaFree(L.parent); cudaFree(L.range); cudaFree(L.arrive); cudaFree(L.emit); cudaFree(L.emit_index); cudaFree(L.cub_tmp);
+    };
+#define LCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    LCK(cudaMalloc(&L.keys, sizeof(uint64_t) * n)); LCK(cudaMalloc(&L.keys_sorted, sizeof(uint64_t) * n));
+    LCK(cudaMalloc(&L.leaf_lo, sizeof(float4) * n)); LCK(cudaMalloc(&L.leaf_hi, sizeof(float4) * n));
+    LCK(cudaMalloc(&L.node_lo, sizeof(float4) * n)); LCK(cudaMalloc(&L.node_hi, sizeof(float4) * n));
+    LCK(cudaMalloc(&L.children, sizeof(int2) * n)); LCK(cudaMalloc(&L.parent, sizeof(int) * 2 * n)); LCK(cudaMalloc(&L.range, sizeof(int2) * n));
+    LCK(cudaMalloc(&L.arrive, sizeof(unsigned) * n)); LCK(cudaMalloc(&L.emit, sizeof(unsigned) * n)); LCK(cudaMalloc(&L.emit_index, sizeof(unsigned) * n));
+    size_t sort_bytes = 0, scan_bytes = 0;
+    LCK(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, L.keys, L.keys_sorted, n, 0, 62, s));
+    LCK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, L.emit, L.emit_index, n - 1, s));
+    L.cub_bytes = std::max(sort_bytes, scan_bytes);
+    LCK(cudaMalloc(&L.cub_tmp, L.cub_bytes));
+    const int B = 256, G = (n + B - 1) / B;
+    float3 lo3 = make_float3(clo[0], clo[1], clo[2]);
+    float3 inv3 = make_float3(chi[0] > clo[0] ? 1.0f / (chi[0] - clo[0]) : 0.f, chi[1] > clo[1] ? 1.0f / (chi[1] - clo[1]) : 0.f,
+                              chi[2] > clo[2] ? 1.0f / (chi[2] - clo[2]) : 0.f);
+    nb::lbvh_keys_kernel<<<G, B, 0, s>>>(c->verts.d, c->faces.d, (unsigned) n, lo3, inv3, L.keys);
+    LCK(cub::DeviceRadixSort::SortKeys(L.cub_tmp, L.cub_bytes, L.keys, L.keys_sorted, n, 0, 62, s));
+    nb::lbvh_leaf_boxes_kernel<<<G, B, 0, s>>>(c->verts.d, c->faces.d, L.keys_sorted, (unsigned) n, pad, L.leaf_lo, L.leaf_hi);
+    nb::lbvh_hierarchy_kernel<<<G, B, 0, s>>>(L.keys_sorted, n, L.children, L.parent, L.range);
+    LCK(cudaMemsetAsync(L.arrive, 0, sizeof(unsigned) * n, s));
+    nb::lbvh_fit_kernel<<<G, B, 0, s>>>(n, L.children, L.parent, L.leaf_lo, L.leaf_hi, L.node_lo, L.node_hi, L.arrive);
+    nb::lbvh_mark_kernel<<<G, B, 0, s>>>(n, L.range, (int) std::max<int64_t>(1, std::min<int64_t>(8, c->opt_max_leaf)), L.emit);
+    LCK(cub::DeviceScan::ExclusiveSum(L.cub_tmp, L.cub_bytes, L.emit, L.emit_index, n - 1, s));
+    unsigned last_idx = 0, last_emit = 0;
+    LCK(cudaMemcpyAsync(&last_idx, L.emit_index + (n - 2), sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    LCK(cudaMemcpyAsync(&last_emit, L.emit + (n - 2), sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    LCK(cudaStreamSynchronize(s));
+    const unsigned nnodes = last_idx + last_emit;
+    if (nnodes == 0) { cleanup(); return fail("LBVH: empty hierarchy"); }
+    LCK(c->nodes.alloc((size_t) nnodes * 4)); LCK(c->tris.alloc((size_t) n * 3));
+    nb::lbvh_emit_nodes_kernel<<<G, B, 0, s>>>(n, L.children, L.range, L.emit, L.emit_index, L.leaf_lo, L.leaf_hi, L.node_lo, L.node_hi, c->nodes.d);
+    nb::lbvh_emit_tris_kernel<<<G, B, 0, s>>>(c->verts.d, c->faces.d, L.keys_sorted, (unsigned) n, c->tris.d);
+    LCK(cudaGetLastError());
+    LCK(cudaMemcpyAsync(c->nodes.h, c->nodes.d, c->nodes.bytes(), cudaMemcpyDeviceToHost, s));
+    LCK(cudaMemcpyAsync(c->tris.h, c->tris.d, c->tris.bytes(), cudaMemcpyDeviceToHost, s));
+    LCK(cudaStreamSynchronize(s));
+#undef LCK
+    cleanup();
+    c->n_nodes = nnodes; c->top_nodes = 0; c->bvh_depth = 0;
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -383,18 +438,55 @@ int nb_build_accel(nb_ctx *c) {
         }
         vo += m.nv; fo += m.nf;
     }
+    c->n_prims = (uint32_t) nf;
+    if (c->opt_builder == 1 && nf > 8) {
+        // ---- device LBVH: upload the mesh tables, then build on the GPU
+        cudaStream_t s = c->stream;
+#define UP(buf) CK(cudaMemcpyAsync(buf.d, buf.h, buf.bytes(), cudaMemcpyHostToDevice, s))
+        UP(c->verts); UP(c->normals); UP(c->uvs); UP(c->faces); UP(c->dmeshes); UP(c->cdf); UP(c->emitters);
+#undef UP
+        float maxabs = 0.f, clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (size_t f = 0; f < nf; ++f) {
+            const uint4 fc = c->faces.h[f];
+            const float4 v[3] = { c->verts.h[fc.x], c->verts.h[fc.y], c->verts.h[fc.z] };
+            const float *p[3] = { &v[0].x, &v[1].x, &v[2].x };
+            for (int a = 0; a < 3; ++a) {
+                const float lo = std::min(p[0][a], std::min(p[1][a], p[2][a])), hi = std::max(p[0][a], std::max(p[1][a], p[2][a]));
+                const float ctr = 0.5f * (lo + hi);
+                clo[a] = std::min(clo[a], ctr); chi[a] = std::max(chi[a], ctr);
+                maxabs = std::max(maxabs, std::max(std::fabs(lo), std::fabs(hi)));
+            }
+        }
+        cudaEvent_t e0 = c->ev[0], e1 = c->ev[3];
+        CK(cudaEventRecord(e0, s));
+        if (build_lbvh_device(c, nf, 4e-6f * maxabs, clo, chi)) return 1;
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        c->build_seconds = ms * 1e-3; c->builder_used = 1;
+        c->built = true;
+        return 0;
+    }
     nb::BvhInput in; in.verts = reinterpret_cast<const float *>(c->verts.h); in.faces = reinterpret_cast<const uint32_t *>(c->faces.h);
     in.nprims = (uint32_t) nf;
     nb::BvhOutput out;
     nb::build_bvh(in, out, (int) c->opt_max_leaf, (uint32_t) c->opt_bfs_nodes, 0);
-    c->n_nodes = out.nnodes; c->n_prims = (uint32_t) nf; c->top_nodes = out.top_nodes; c->bvh_depth = out.depth;
-    c->build_seconds = out.build_seconds;
+    c->n_nodes = out.nnodes; c->top_nodes = out.top_nodes; c->bvh_depth = out.depth;
+    c->build_seconds = out.build_seconds; c->builder_used = 0;
     if (out.depth >= nb::kStack) return fail("BVH too deep (%d)", out.depth);
     CK(c->nodes.alloc((size_t) out.nnodes * 4)); CK(c->tris.alloc(out.tris.size() / 4));
     memcpy(c->nodes.h, out.nodes.data(), out.nodes.size() * sizeof(float));
     if (!out.tris.empty()) memcpy(c->tris.h, out.tris.data(), out.tris.size() * sizeof(float));
     c->built = true;
     return nb_upload_scene(c);
+}
+
+int nb_build_stats(nb_ctx *c, double *seconds, int *builder) {
+    if (!c) return fail("null context");
+    if (!c->built) return fail("nb_build_accel has not been called");
+    if (seconds) *seconds = c->build_seconds;
+    if (builder) *builder = c->builder_used;
+    return 0;
 }
 
 int nb_set_camera(nb_ctx *c, const float s2c[16], const float c2w[16], int width, int height, float nearClip, float farClip) {
@@ -595,6 +687,7 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     else if (k == "count") c->opt_count = value;
     else if (k == "max_leaf") { c->opt_max_leaf = value; c->built = false; }
     else if (k == "bfs_nodes") { c->opt_bfs_nodes = value; c->built = false; }
+    else if (k == "builder") { if (value != 0 && value != 1) return fail("builder must be 0 (host SAH) or 1 (device LBVH)"); c->opt_builder = value; c->built = false; }
     else return fail("unknown option \"%s\"", key);
     return 0;
 }
