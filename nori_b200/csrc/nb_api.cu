@@ -470,7 +470,7 @@ int nb_build_accel(nb_ctx *c) {
     nb::BvhInput in; in.verts = reinterpret_cast<const float *>(c->verts.h); in.faces = reinterpret_cast<const uint32_t *>(c->faces.h);
     in.nprims = (uint32_t) nf;
     nb::BvhOutput out;
-    nb::build_bvh(in, out, (int) c->opt_max_leaf, (uint32_t) c->opt_bfs_nodes, 0);
+    nb::build_bvh(in, out, (int) c->opt_max_leaf, c->opt_bfs_nodes < 0 ? nb::kSiblingPairs : (uint32_t) c->opt_bfs_nodes, 0);
     c->n_nodes = out.nnodes; c->top_nodes = out.top_nodes; c->bvh_depth = out.depth;
     c->build_seconds = out.build_seconds; c->builder_used = 0;
     if (out.depth >= nb::kStack) return fail("BVH too deep (%d)", out.depth);

@@ -268,6 +268,24 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
         std::vector<uint32_t> final_order;   // build-node ids of inner nodes in final order
         final_order.reserve(n);
         std::vector<int32_t> final_index(b.nnodes.load(), -1);
+        constexpr uint32_t kHole = 0xffffffffu;      // padding slot (sibling-pair layout)
+        if (bfs_nodes == kSiblingPairs) {
+            // Sibling-pair layout: the two inner children of a node occupy one aligned 128-byte line (two 64 B nodes), so
+            // the walk's later pop of the far child hits the line its near sibling already brought into L1.
+            final_index[0] = 0; final_order.push_back(0);
+            std::vector<uint32_t> stack; stack.push_back(0);
+            while (!stack.empty()) {
+                uint32_t id = stack.back(); stack.pop_back();
+                const BNode &nd = b.nodes[id];
+                const bool li = b.nodes[nd.left].count == 0, ri = b.nodes[nd.right].count == 0;
+                if (li && ri && (final_order.size() & 1u)) final_order.push_back(kHole);
+                if (li) { final_index[nd.left] = (int32_t) final_order.size(); final_order.push_back(nd.left); }
+                if (ri) { final_index[nd.right] = (int32_t) final_order.size(); final_order.push_back(nd.right); }
+                if (ri) stack.push_back(nd.right);
+                if (li) stack.push_back(nd.left);
+            }
+            out.top_nodes = 0;
+        } else {
         std::vector<uint32_t> queue; queue.push_back(0);
         size_t qh = 0;
         while (qh < queue.size() && final_order.size() < bfs_nodes) {
@@ -289,12 +307,14 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
             if (b.nodes[nd.right].count == 0) stack.push_back(nd.right);
             if (b.nodes[nd.left].count == 0) stack.push_back(nd.left);
         }
+        }
         out.nnodes = (uint32_t) final_order.size();
         out.nodes.assign((size_t) out.nnodes * 16, 0.f);
         // leaf triangle offsets in final node order (sequential prefix), then nodes + triangles are written in parallel
         std::vector<uint32_t> leaf_first((size_t) out.nnodes * 2, 0);
         uint32_t tri_cursor = 0;
         for (uint32_t fi = 0; fi < out.nnodes; ++fi) {
+            if (final_order[fi] == kHole) continue;
             const BNode &nd = b.nodes[final_order[fi]];
             out.depth = std::max(out.depth, nd.depth + 2);
             const uint32_t ch[2] = { nd.left, nd.right };
@@ -306,6 +326,7 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
         out.tris.assign((size_t) tri_cursor * 12, 0.f);
         auto fill = [&](uint32_t fb, uint32_t fe, int) {
             for (uint32_t fi = fb; fi < fe; ++fi) {
+                if (final_order[fi] == kHole) continue;      // padding slot: never referenced, stays zero
                 const BNode &nd = b.nodes[final_order[fi]];
                 float *o = out.nodes.data() + (size_t) fi * 16;
                 const uint32_t ch[2] = { nd.left, nd.right };

@@ -37,7 +37,9 @@ struct BvhOutput {
     double build_seconds = 0;
 };
 
-// max_leaf in 1..8; bfs_nodes: how many leading nodes to lay out breadth-first; nthreads <= 0: hardware concurrency
+// max_leaf in 1..8; bfs_nodes: how many leading nodes to lay out breadth-first (kSiblingPairs: sibling-pair layout instead,
+// the two inner children of a node share one aligned 128-byte line); nthreads <= 0: hardware concurrency
+constexpr uint32_t kSiblingPairs = 0xffffffffu;
 void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf = 4, uint32_t bfs_nodes = 2048, int nthreads = 0);
 
 }  // namespace nb
