@@ -196,45 +196,39 @@ __device__ __forceinline__ float mf_G1(V3 wv, V3 wh, float alpha) {
     return (3.535f * b + 2.181f * b2) / (1.0f + 2.276f * b + 2.577f * b2);
 }
 
-__device__ __noinline__ V3 bsdf_eval(const DevMesh &m, V3 wi, V3 wo) {
-    if (m.bsdf_type == 0) {            // ref: src/diffuse.cpp:23-33
+// eval() and pdf() of the same (wi, wo) in one pass.  The microfacet terms they share (half vector, Beckmann D) are
+// computed once; every value is produced by the same operation sequence as the separate functions of the oracle
+// (oracle.c: bsdf_eval / bsdf_pdf), so the results are bit-identical.
+__device__ __noinline__ V3 bsdf_eval_pdf(const DevMesh &m, V3 wi, V3 wo, float &pdf) {
+    pdf = 0.0f;
+    if (m.bsdf_type == 0) {            // ref: src/diffuse.cpp:23-33, 36-52
         if (wi.z <= 0 || wo.z <= 0) return mk(0, 0, 0);
+        pdf = NB_INV_PI * wo.z;
         return mk(m.albedo[0] * NB_INV_PI, m.albedo[1] * NB_INV_PI, m.albedo[2] * NB_INV_PI);
     }
-    if (m.bsdf_type == 3) {            // [authored] contract ref: src/microfacet.cpp:40-42
+    if (m.bsdf_type == 3) {            // [authored] contract ref: src/microfacet.cpp:40-47
         if (wi.z <= 0 || wo.z <= 0) return mk(0, 0, 0);
-        V3 wh = normalize(wi + wo);
-        float D = beckmann_D(wh, m.alpha);
-        float F = fresnel(dot(wh, wi), m.extIOR, m.intIOR);
-        float G = mf_G1(wi, wh, m.alpha) * mf_G1(wo, wh, m.alpha);
-        float spec = m.ks * D * F * G / (4.0f * wi.z * wo.z);
+        const V3 wh = normalize(wi + wo);
+        const float D = beckmann_D(wh, m.alpha);
+        const float F = fresnel(dot(wh, wi), m.extIOR, m.intIOR);
+        const float G = mf_G1(wi, wh, m.alpha) * mf_G1(wo, wh, m.alpha);
+        const float spec = m.ks * D * F * G / (4.0f * wi.z * wo.z);
+        const float Jh = 1.0f / (4.0f * dot(wh, wo));
+        pdf = m.ks * D * wh.z * Jh + (1.0f - m.ks) * wo.z * NB_INV_PI;
         return mk(m.albedo[0] * NB_INV_PI + spec, m.albedo[1] * NB_INV_PI + spec, m.albedo[2] * NB_INV_PI + spec);
     }
-    return mk(0, 0, 0);                // discrete: ref src/mirror.cpp:17-20, src/dielectric.cpp:23-26
-}
-
-__device__ __noinline__ float bsdf_pdf(const DevMesh &m, V3 wi, V3 wo) {
-    if (m.bsdf_type == 0) {            // ref: src/diffuse.cpp:36-52
-        if (wi.z <= 0 || wo.z <= 0) return 0.0f;
-        return NB_INV_PI * wo.z;
-    }
-    if (m.bsdf_type == 3) {
-        if (wi.z <= 0 || wo.z <= 0) return 0.0f;
-        V3 wh = normalize(wi + wo);
-        float D = beckmann_D(wh, m.alpha);
-        float Jh = 1.0f / (4.0f * dot(wh, wo));
-        return m.ks * D * wh.z * Jh + (1.0f - m.ks) * wo.z * NB_INV_PI;
-    }
-    return 0.0f;
+    return mk(0, 0, 0);                // discrete: ref src/mirror.cpp:17-24, src/dielectric.cpp:23-30
 }
 
 // returns weight = eval*cos/pdf (0 <=> invalid); measure: 1 solid angle, 2 discrete
-__device__ __noinline__ V3 bsdf_sample(const DevMesh &m, V3 wi, float xi_x, float xi_y, V3 &wo, int &measure) {
-    measure = 1; wo = mk(0, 0, 1);
+// `pdf` receives pdf(wi, wo) of the sampled direction (0 for discrete lobes and invalid samples)
+__device__ __noinline__ V3 bsdf_sample(const DevMesh &m, V3 wi, float xi_x, float xi_y, V3 &wo, int &measure, float &pdf) {
+    measure = 1; wo = mk(0, 0, 1); pdf = 0.0f;
     switch (m.bsdf_type) {
         case 0:                        // ref: src/diffuse.cpp:55-71
             if (wi.z <= 0) return mk(0, 0, 0);
             wo = square_to_cosine_hemisphere(xi_x, xi_y);
+            pdf = wo.z <= 0 ? 0.0f : NB_INV_PI * wo.z;                  // == bsdf_pdf(diffuse): ref src/diffuse.cpp:36-52
             return mk(m.albedo[0], m.albedo[1], m.albedo[2]);
         case 1:                        // ref: src/mirror.cpp:27-43
             if (wi.z <= 0) return mk(0, 0, 0);
@@ -266,9 +260,10 @@ __device__ __noinline__ V3 bsdf_sample(const DevMesh &m, V3 wi, float xi_x, floa
                 wo = square_to_cosine_hemisphere(x, xi_y);
             }
             if (wo.z <= 0) return mk(0, 0, 0);
-            V3 f = bsdf_eval(m, wi, wo);
-            float p = bsdf_pdf(m, wi, wo);
+            float p;
+            const V3 f = bsdf_eval_pdf(m, wi, wo, p);
             if (!(p > 0.0f)) return mk(0, 0, 0);
+            pdf = p;
             return mk(f.x * wo.z / p, f.y * wo.z / p, f.z * wo.z / p);
         }
     }

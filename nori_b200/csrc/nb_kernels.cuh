@@ -446,8 +446,8 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
         const float x = pcg_next_float(ps.rng);
         if (x >= 0.95f) return true;
         const float sx = pcg_next_float(ps.rng), sy = pcg_next_float(ps.rng);
-        V3 wo; int measure;
-        const V3 f = bsdf_sample(m, wi, sx, sy, wo, measure);
+        V3 wo; int measure; float spdf;
+        const V3 f = bsdf_sample(m, wi, sx, sy, wo, measure, spdf);
         if (is_zero(f)) return true;
         ps.T = mk(ps.T.x * f.x / 0.95f, ps.T.y * f.y / 0.95f, ps.T.z * f.z / 0.95f);
         const V3 d = to_world(its.sh, wo);
@@ -476,11 +476,12 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
         const float cosL = -dot(es.n, wo_w);
         if (cosL > 0.0f) {
             const V3 wo = to_local(its.sh, wo_w);
-            const V3 f = bsdf_eval(m, wi, wo);
+            float bpdf;
+            const V3 f = bsdf_eval_pdf(m, wi, wo, bpdf);
             if (!is_zero(f)) {
                 const float pdf_sa = es.pdfA * dist2 / cosL;
                 float w = 1.0f;
-                if (INTEG == 5) w = pdf_sa / (pdf_sa + bsdf_pdf(m, wi, wo));
+                if (INTEG == 5) w = pdf_sa / (pdf_sa + bpdf);
                 const float g = wo.z / pdf_sa * w;
                 ps.contrib = mk(ps.T.x * f.x * es.Le.x * g, ps.T.y * f.y * es.Le.y * g, ps.T.z * f.z * es.Le.z * g);
                 sray.dx = wo_w.x; sray.dy = wo_w.y; sray.dz = wo_w.z; sray.mint = NB_EPSILON; sray.maxt = dist - NB_EPSILON;
@@ -491,12 +492,12 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
     ps.has_next = false;
     if (INTEG != 2) {                                   // BSDF sampling -> extension ray
         const float sx = pcg_next_float(ps.rng), sy = pcg_next_float(ps.rng);
-        V3 wo; int measure;
-        const V3 f = bsdf_sample(m, wi, sx, sy, wo, measure);
+        V3 wo; int measure; float spdf;
+        const V3 f = bsdf_sample(m, wi, sx, sy, wo, measure, spdf);
         if (!is_zero(f)) {
             ps.T = ps.T * f;
             ps.prev_specular = (measure == 2);
-            ps.prev_pdf = ps.prev_specular ? 0.0f : bsdf_pdf(m, wi, wo);
+            ps.prev_pdf = ps.prev_specular ? 0.0f : spdf;            // == bsdf_pdf(wi, wo) of the sampled direction
             ps.next_d = to_world(its.sh, wo);
             ps.depth++;
             ps.has_next = ps.depth < P.max_depth;
