@@ -136,7 +136,7 @@ int nb_render_device(nb_ctx *, float *film_dev, void *stream, nb_stats *stats);
 
 /* Finished ImageBlocks of this context's tiles, packed: blocks_dev receives ntiles_mine x (32+2b) x (32+2b) x 4 fp32
  * (tile order = ascending tile_id of the tiles owned by (rank, nranks)); the frame-end exchange gathers these. */
-int nb_render_blocks_device(nb_ctx *, float *blocks_dev, void *stream, nb_stats *stats);
+int nb_render_blocks_device(nb_ctx *, float *blocks_dev, void *stream, nb_stats *stats);   /* stats == NULL: enqueue only, no host sync */
 /* Number of tiles owned by (rank, nranks) for the current camera, and the block edge (32 + 2*border). */
 int nb_tile_count(nb_ctx *, int rank, int nranks, int *ntiles, int *block_edge);
 /* Adds packed blocks of (rank, nranks) into a full film on the device: the merge of ImageBlock::put(ImageBlock&)

@@ -212,7 +212,11 @@ class Context:
         _check(lib().nb_render_device(self.h, C.c_void_p(film_ptr), C.c_void_p(stream), C.byref(st)))
         return st
 
-    def render_blocks_device(self, blocks_ptr: int, stream: int = 0):
+    def render_blocks_device(self, blocks_ptr: int, stream: int = 0, want_stats: bool = True):
+        """want_stats=False only enqueues the work on `stream` (no counter read-back, no host synchronisation)."""
+        if not want_stats:
+            _check(lib().nb_render_blocks_device(self.h, C.c_void_p(blocks_ptr), C.c_void_p(stream), None))
+            return None
         st = Stats()
         _check(lib().nb_render_blocks_device(self.h, C.c_void_p(blocks_ptr), C.c_void_p(stream), C.byref(st)))
         return st

@@ -542,6 +542,7 @@ int nb_render_blocks_device(nb_ctx *c, float *blocks_dev, void *stream, nb_stats
     if (!c || !blocks_dev) return fail("null argument");
     cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
     if (render_blocks(c, reinterpret_cast<float4 *>(blocks_dev), s, st, nullptr)) return 1;
+    if (!st) return 0;               // fire and forget: no counter read-back, no host synchronisation
     return finish_stats(c, s, st, 0);
 }
 
