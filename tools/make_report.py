@@ -10,9 +10,9 @@ def load(name):
     return json.load(open(p)) if os.path.exists(p) else None
 
 
-rows = [("configs[1] Ajax(stand-in) ao 800x600x64", "r1_v6_bench.json", "configs[1]"),
-        ("configs[2] Cornell box path_mis 512x512x256", "r1_v6_bench_cbox-mis.json", "configs[2]"),
-        ("configs[3] Ajax(stand-in) microfacet path_mis 768x768x1024", "r1_v6_bench_ajax-rough.json", "configs[3]"),
+rows = [("configs[1] Ajax(stand-in) ao 800x600x64", "r1_final_bench.json", "configs[1]"),
+        ("configs[2] Cornell box path_mis 512x512x256", "r1_final_bench_cbox-mis.json", "configs[2]"),
+        ("configs[3] Ajax(stand-in) microfacet path_mis 768x768x1024", "r1_final_bench_ajax-rough.json", "configs[3]"),
         ("configs[4] 10 M random triangles ao 1920x1080x4", "r1_v4_bench_random10m-ao.json", "configs[4]"),
         ("configs[4] 10 M random triangles normals 1920x1080x4", "r1_v4_bench_random10m-normals.json", None)]
 parity = {}
@@ -32,7 +32,7 @@ for title, fn, pk in rows:
     if not d:
         continue
     r = d["roofline"]
-    wl = {"r1_v6_bench.json": "ajax-ao", "r1_v4_bench_random10m-ao.json": "random10m-ao"}.get(fn)
+    wl = {"r1_final_bench.json": "ajax-ao", "r1_v4_bench_random10m-ao.json": "random10m-ao"}.get(fn)
     dram = "n/a"
     if wl and wl in traffic:
         dram = "%.0f" % (traffic[wl]["bytes"] / (r["kernel_ms"] * 1e-3) / 1e9)
@@ -48,7 +48,7 @@ out += ["", "rel-L2 for configs[2..4] was measured at reduced spp / 1 M triangle
         "configs[1] and configs[0] at full size.  Ray counts of GPU and oracle are identical in every case.", "",
         "## CPU arm on the same box (128 host cores; oracle port of the Nori tile loop, `bench.py --impl reference`)", "",
         "| workload | accel | Mrays/s | Msamples/s | s / step |", "|---|---|---|---|---|"]
-for title, fn, acc in [("configs[1] ajax-ao at 32 of 64 spp per step", "r1_v6_bench_ref.json", "CPU binned-SAH BVH"),
+for title, fn, acc in [("configs[1] ajax-ao at 32 of 64 spp per step", "r1_final_bench_ref.json", "CPU binned-SAH BVH"),
                        ("configs[0] bunny 768x768x1", "r1_v6_bench_ref_brute_bunny.json", "brute force (the reference's shipped Accel)")]:
     d = load(fn)
     if d:
