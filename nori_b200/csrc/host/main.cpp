@@ -8,7 +8,7 @@ using namespace nori;
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N]" << endl;
+        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N] [--lbvh]" << endl;
         return -1;
     }
     std::string sceneName;
@@ -19,6 +19,8 @@ int main(int argc, char **argv) {
             if (i + 1 >= argc) { cerr << "\"--threads\" argument expects a positive integer following it." << endl; return -1; }
             ++i;   // accepted, unused
         } else if (token == "--no-gui") {
+        } else if (token == "--lbvh") {
+            opt.deviceBuilder = true;   // GPU-built hierarchy (fast build, slightly slower render)
         } else if (token == "--device") {
             if (i + 1 >= argc) { cerr << "\"--device\" expects an integer following it." << endl; return -1; }
             opt.device = atoi(argv[++i]);

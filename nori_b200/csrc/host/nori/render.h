@@ -12,6 +12,7 @@ struct RenderOptions {
     int device = 0;            // CUDA device of this process
     int tileRank = 0, tileRanks = 1;   // tile shard (multi-GPU: one process per GPU)
     bool quiet = false;
+    bool deviceBuilder = false;        // build the hierarchy on the GPU (LBVH) instead of the host SAH builder
 };
 
 /// Builds the GPU context for a scene: meshes + plugin descriptors (from the factory's creation records), BVH,

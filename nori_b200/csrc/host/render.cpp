@@ -74,6 +74,7 @@ nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const Rend
     nb_ctx *ctx = nb_create(opt.device);
     if (!ctx) throwLast("nb_create");
     try {
+        if (opt.deviceBuilder && nb_set_option(ctx, "builder", 1)) throwLast("nb_set_option");
         for (const Mesh *mesh : scene->getMeshes()) {   // Scene::addChild(mesh) -> Accel::addMesh (ref: src/scene.cpp:48-53)
             nb_bsdf_desc b = describeBSDF(mesh->getBSDF());
             nb_emitter_desc e;
