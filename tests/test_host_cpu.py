@@ -88,6 +88,13 @@ def test_lookat_rotate_and_defaults(tmp_path):
     ('<scene><integrator type="ao"></scene>', "mismatched closing tag"),
     ('<scene><mesh type="obj"><string name="filename" value="missing.obj"/></mesh></scene>', "Unable to open OBJ file"),
     ('<scene><mesh type="obj"><emitter type="area"/></mesh></scene>', "Property 'radiance' is missing!"),
+    ('<scene><integrator type="ao"/><camera type="perspective"><integer name="fov" value="30"/></camera></scene>', "Property 'fov' has the wrong type! (expected <float>)!"),
+    ('<scene><integrator type="ao"/><camera type="perspective"><boolean name="x" value="maybe"/></camera></scene>', 'Could not parse boolean value "maybe"'),
+    ('<scene><integrator type="ao"/><camera type="perspective"><transform name="toWorld"><matrix value="1 0 0"/></transform></camera></scene>', "Expected 16 values"),
+    ('<scene><integrator type="ao"/><sampler type="independent"/><sampler type="independent"/></scene>', "There can only be one sampler per scene!"),
+    ('<scene><integrator type="ao"/><camera type="perspective"><rfilter type="box"/><rfilter type="tent"/></camera></scene>', "tried to register multiple reconstruction filters"),
+    ('<scene><integrator type="ao"/><bsdf type="diffuse"/></scene>', "Scene::addChild(<bsdf>) is not supported!"),
+    ('<scene><integrator type="ao"/><sampler type="independent"><string name="seedMode" value="lattice"/></sampler></scene>', 'unknown seedMode "lattice"'),
 ])
 def test_parser_errors(tmp_path, xml, msg):
     p = tmp_path / "bad.xml"
