@@ -31,6 +31,9 @@ def test_reference_scene_bunny_through_cli(tmp_path, oracle):
     """BASELINE configs[0] end to end through the `nori` executable: XML in, EXR + PNG out."""
     sc = S.config_bunny()      # 768x768, 1 spp, normals, per-block seeding
     path = host.write_xml(sc, str(tmp_path), "bunny")
+    if not os.path.exists(host.CLI_PATH):          # the executable is a g++-only artefact: rebuild it if the snapshot lost it
+        from nori_b200 import build as nb_build
+        nb_build.build_host(force=True)
     r = subprocess.run([host.CLI_PATH, path, "--no-gui", "--threads", "4"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Rendering .. done." in r.stdout
