@@ -34,6 +34,12 @@ namespace nb {
 #ifndef NB_WALK_NOINLINE
 #define NB_WALK_NOINLINE 0
 #endif
+#ifndef NB_PHASED_WAVES
+#define NB_PHASED_WAVES 1
+#endif
+#ifndef NB_PHASED_AO
+#define NB_PHASED_AO 0       // measured on ajax-ao: see profiles/r1_final_summary.md
+#endif
 #ifndef NB_SPLAT_HOIST
 #define NB_SPLAT_HOIST 1
 #endif
@@ -574,13 +580,13 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
     unsigned wave_nodes = 0; unsigned long long wave_max_sum = 0, n_waves = 0;
 
     // warp-uniform work-unit state
-    bool exhausted = false;
+    bool exhausted = false, traced = false;
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
 
     for (;;) {
         // ---- shading phase (lock step: every lane's ray is finished here)
-        if (ps.stage != ST_IDLE) {
+        if (ps.stage != ST_IDLE && traced) {
             const bool finished = shade<INTEG>(P, ps, ray, tr, n_hits);
             if (finished) {
                 splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
@@ -632,8 +638,16 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
             need_mask = __ballot_sync(0xffffffffu, need);
         }
         if (__ballot_sync(0xffffffffu, ps.stage != ST_IDLE) == 0u) break;     // work exhausted and every path retired
-        // ---- traversal phase: every active lane walks its ray to completion
-        if (ps.stage != ST_IDLE) {
+        // ---- traversal phase: every active lane walks its ray to completion.  Path integrators run PHASED waves
+        // (NB_PHASED_WAVES): if any lane holds a shadow ray the wave traces shadow rays only, else extension rays only;
+        // lanes holding the other kind keep their ray and wait.  Shading after a wave is then stage-homogeneous
+        // (all NEE-resolve or all hit-shade) instead of a 50/50 mix, and any-hit waves are not held up by closest-hit.
+        traced = (ps.stage != ST_IDLE);
+        if (NB_PHASED_WAVES && (INTEG >= 2 || (NB_PHASED_AO && INTEG == 1))) {
+            const bool any_shadow = __ballot_sync(0xffffffffu, ps.stage >= ST_SHADOW) != 0u;
+            traced = any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND);
+        }
+        if (traced) {
             const WalkResult w = walk<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray.ox, ray.oy, ray.oz, ray.mint,
                                                       ray.dx, ray.dy, ray.dz, ray.maxt, ps.stage != ST_EXTEND);
             ray.maxt = w.t; tr.hu = w.u; tr.hv = w.v; tr.hprim = w.prim;
