@@ -78,7 +78,7 @@ struct nb_ctx {
     unsigned long long *counters_h = nullptr;        // pinned
     // options
     int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 0, opt_count = 0, opt_max_leaf = 3,
-            opt_bfs_nodes = 2048, opt_builder = 0;
+            opt_bfs_nodes = 2048, opt_builder = 0, opt_tail = 0;
     int builder_used = 0;   // 0 host SAH, 1 device LBVH
 };
 
@@ -176,6 +176,7 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     // Reference per-block streams are sequential by construction; only `normals` consumes a fixed number of draws per
     // sample (4), which lets the parallel kernel jump to each sample's stream position (pcg32 skip-ahead).
     P.block_stream_skip = (c->seed_mode == NB_SEED_PER_BLOCK && c->integ.type == NB_INT_NORMALS) ? 1 : 0;
+    P.tail_lanes = (int32_t) c->opt_tail;
     const bool block_mode = c->seed_mode == NB_SEED_PER_BLOCK && !P.block_stream_skip;
     const bool count = c->opt_count != 0;
     P.smem_nodes = (block_mode || count) ? 0 : (int) std::min<int64_t>(std::min<int64_t>(c->opt_smem_nodes, c->top_nodes), 3400);
@@ -686,6 +687,7 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     else if (k == "smem_nodes") c->opt_smem_nodes = value;
     else if (k == "chunk") c->opt_chunk = value;
     else if (k == "count") c->opt_count = value;
+    else if (k == "tail") { if (value < 0 || value > 31) return fail("tail must be in [0, 31]"); c->opt_tail = value; }
     else if (k == "max_leaf") { c->opt_max_leaf = value; c->built = false; }
     else if (k == "bfs_nodes") { c->opt_bfs_nodes = value; c->built = false; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail("builder must be 0 (host SAH) or 1 (device LBVH)"); c->opt_builder = value; c->built = false; }

@@ -38,7 +38,10 @@ namespace nb {
 #define NB_PHASED_WAVES 1
 #endif
 #ifndef NB_PHASED_AO
-#define NB_PHASED_AO 0       // measured on ajax-ao: see profiles/r1_final_summary.md
+#define NB_PHASED_AO 1       // ajax-ao 9.59 -> 9.20 ms, random10m-ao 11.8 -> 11.2 ms (profiles/r1_final_summary.md)
+#endif
+#ifndef NB_TAIL_CUT
+#define NB_TAIL_CUT 0        // resumable walks + "tail" option; costs registers (cbox-mis +7 % at tail=0), gain not yet measured
 #endif
 #ifndef NB_SPLAT_HOIST
 #define NB_SPLAT_HOIST 1
@@ -83,6 +86,7 @@ struct RenderParams {
     unsigned long long *counters;   // [0] next unit, [1] rays, [2] node visits, [3] tri tests, [4] hits shaded
     int32_t smem_nodes;             // nodes staged in shared memory (0 = none)
     int32_t block_stream_skip;      // per-block seeding served by skip-ahead (fixed draws per sample)
+    int32_t tail_lanes;             // a wave's walk is suspended once <= tail_lanes lanes are still walking (0 = never)
 };
 
 // ------------------------------------------------------------------ traversal state (per lane)
@@ -162,9 +166,10 @@ __device__ __forceinline__ bool leaf_test(const SceneDev &sc, int leaf, Ray &r, 
 
 template <bool COUNT, bool TMA_TOP>
 __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snodes, int smem_nodes, Ray &r, Trav &t,
-                                         int *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris) {
+                                         int *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris, int tail = 0) {
     int node = t.node, sp = t.sp;
     int parked = 0;                  // postponed leaf ref (leaf refs are negative; 0 = none)
+    bool suspended = false;
 #if NB_SPECULATIVE >= 2
     int parked2 = 0;
 #endif
@@ -226,8 +231,35 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
         if (leaf_test<COUNT>(sc, node, r, t, any_hit, n_tris)) break;
         node = sp ? stack[--sp] : kDone;
 #endif
+#if NB_TAIL_CUT
+        // ---- tail cut (experimental): when only a few lanes of the warp are still walking, they
+        // keep their (node, stack) and the warp goes on to shade / refill the finished lanes; the walk resumes in the next
+        // wave.  Checked at the END of an iteration so that every call makes progress (a check on entry livelocks as soon
+        // as a wave starts with <= tail lanes).
+        if (tail > 0 && (node != kDone || parked != 0) && __popc(__activemask()) <= tail) {
+            if (parked != 0) { if (node != kDone) stack[sp++] = node; node = parked; }
+            suspended = true;
+            break;
+        }
+#endif
     }
-    t.node = kDone; t.sp = 0;
+    if (suspended) { t.node = node; t.sp = sp; } else { t.node = kDone; t.sp = 0; }
+}
+
+// Resumable walk for the render kernel: tr.node == kDone on entry means a fresh ray; otherwise (node, sp, stack) and the
+// closest hit so far continue from where a tail cut suspended them.  The slab-test reciprocals are recomputed per call
+// so that only (node, sp, hit) stay live across the shading phase.
+template <bool COUNT, bool TMA_TOP>
+__device__ __forceinline__ void walk_wave(const float4 *nodes, const float4 *tris, const float4 *snodes, int smem_nodes,
+                                          Ray &ray, Trav &tr, int *stack, bool any_hit, int tail, unsigned &nn, unsigned &nt) {
+    SceneDev sc;
+    sc.nodes = nodes; sc.tris = tris;
+    const int node = tr.node, sp = tr.sp;
+    const uint32_t hp = tr.hprim; const float hu = tr.hu, hv = tr.hv;
+    Trav t; trav_begin(ray, t);
+    if (node != kDone) { t.node = node; t.sp = sp; t.hprim = hp; t.hu = hu; t.hv = hv; }
+    trav_run<COUNT, TMA_TOP>(sc, snodes, smem_nodes, ray, t, stack, any_hit, nn, nt, tail);
+    tr.node = t.node; tr.sp = t.sp; tr.hprim = t.hprim; tr.hu = t.hu; tr.hv = t.hv;
 }
 
 // Entry to the walk (one call per ray).  NB_WALK_NOINLINE=1 compiles it as a real function with its own register
@@ -573,7 +605,9 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    // (the traversal stack lives inside walk())
+#if NB_TAIL_CUT
+    int stack[kStack];            // per-lane traversal stack (local memory); survives a tail cut
+#endif
     Path ps; Ray ray; Trav tr;
     ps.stage = ST_IDLE; tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu;
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
@@ -586,7 +620,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
 
     for (;;) {
         // ---- shading phase (lock step: every lane's ray is finished here)
-        if (ps.stage != ST_IDLE && traced) {
+        if (ps.stage != ST_IDLE && traced && (!NB_TAIL_CUT || tr.node == kDone)) {
             const bool finished = shade<INTEG>(P, ps, ray, tr, n_hits);
             if (finished) {
                 splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
@@ -645,13 +679,21 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
         traced = (ps.stage != ST_IDLE);
         if (NB_PHASED_WAVES && (INTEG >= 2 || (NB_PHASED_AO && INTEG == 1))) {
             const bool any_shadow = __ballot_sync(0xffffffffu, ps.stage >= ST_SHADOW) != 0u;
-            traced = any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND);
+            traced = (any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND));
+            if (NB_TAIL_CUT) traced = traced || (ps.stage != ST_IDLE && tr.node != kDone);
         }
         if (traced) {
+#if NB_TAIL_CUT
+            unsigned nn = 0, nt = 0;
+            walk_wave<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray, tr, stack, ps.stage != ST_EXTEND,
+                                      exhausted ? 0 : P.tail_lanes, nn, nt);
+            if (COUNT) { n_nodes += nn; n_tris += nt; wave_nodes = nn; }
+#else
             const WalkResult w = walk<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray.ox, ray.oy, ray.oz, ray.mint,
                                                       ray.dx, ray.dy, ray.dz, ray.maxt, ps.stage != ST_EXTEND);
             ray.maxt = w.t; tr.hu = w.u; tr.hv = w.v; tr.hprim = w.prim;
             if (COUNT) { n_nodes += w.n_nodes; n_tris += w.n_tris; wave_nodes = w.n_nodes; }
+#endif
         }
         if (COUNT) {
             // lock-step diagnostics: per wave, the longest walk (what the warp pays) vs the sum over lanes (what it needs)
