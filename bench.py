@@ -315,7 +315,8 @@ def main():
                     "what": "nb_upload_scene (scene arrays from pinned host memory) + nb_render into a host film"},
             "gpu_launches": int(args.steps * (world + 1)),   # per step: one render_kernel per rank + one merge kernel on rank 0
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload) if world == 1 else None, "peak_source": peak_src, "kernel": "render_kernel<ao>",
+                         "traffic": ncu_traffic(args.workload) if world == 1 else None, "peak_source": peak_src,
+                         "kernel": "render_kernel<%s>" % {v: k for k, v in S.INTEGRATORS.items()}[scene.integrator],
                          "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_launch": alg_bytes / world,
                          "node_visits": tot_nodes, "tri_tests": tot_tris, "hits_shaded": tot_hits,
                          "note": "scene (%.0f MB) is L2-resident: this is EFFECTIVE bandwidth of the traversal, see profiles/ for DRAM bytes" % (info["bytes"] / 1e6)},
