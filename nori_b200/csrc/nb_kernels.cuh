@@ -43,6 +43,9 @@ namespace nb {
 #ifndef NB_TAIL_CUT
 #define NB_TAIL_CUT 0        // resumable walks + "tail" option; costs registers (cbox-mis +7 % at tail=0), gain not yet measured
 #endif
+#ifndef NB_COMPACT_PATH
+#define NB_COMPACT_PATH 0    // experiment: keep only tile_slot per lane, re-derive the tile rectangle at splat time
+#endif
 #ifndef NB_SPLAT_HOIST
 #define NB_SPLAT_HOIST 1
 #endif
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
 #if NB_TAIL_CUT
-    int stack[kStack];            // per-lane traversal stack (local memory); survives a tail cut
+    int stack[kStack + 1];        // per-lane traversal stack (local memory); survives a tail cut (+1: a parked leaf is pushed back)
 #endif
     Path ps; Ray ray; Trav tr;
     ps.stage = ST_IDLE; tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu;
@@ -623,7 +626,15 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
         if (ps.stage != ST_IDLE && traced && (!NB_TAIL_CUT || tr.node == kDone)) {
             const bool finished = shade<INTEG>(P, ps, ray, tr, n_hits);
             if (finished) {
+#if NB_COMPACT_PATH
+                {   // tile geometry re-derived from the slot instead of carried per lane through the walk
+                    const int tile_id = P.tile_rank + ps.tile_slot * P.tile_nranks;
+                    const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+                    splat(P, ps.tile_slot, tox, toy, min(32, P.W - tox), min(32, P.H - toy), ps.sx, ps.sy, ps.L);
+                }
+#else
                 splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
+#endif
                 ps.stage = ST_IDLE;
             } else {
                 n_rays++;
@@ -662,8 +673,11 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
                 const uint32_t item = next_item + rank;
                 const uint32_t pix_slot = item % n_valid, s = sample_base + item / n_valid;
                 const int pl = __fns(valid_mask, 0, pix_slot + 1);      // lane index of the pix_slot-th valid pixel
-                ps.tile_slot = u_tile_slot; ps.tox = (short) u_tox; ps.toy = (short) u_toy;
+                ps.tile_slot = u_tile_slot;
+#if !NB_COMPACT_PATH
+                ps.tox = (short) u_tox; ps.toy = (short) u_toy;
                 ps.tsx = (unsigned char) u_tsx; ps.tsy = (unsigned char) u_tsy;
+#endif
                 begin_path(P, ps, ray, u_px0 + (pl & 7), u_py0 + (pl >> 3), s);
                 n_rays++;
                 need = false;
@@ -678,9 +692,16 @@ __global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLO
         // (all NEE-resolve or all hit-shade) instead of a 50/50 mix, and any-hit waves are not held up by closest-hit.
         traced = (ps.stage != ST_IDLE);
         if (NB_PHASED_WAVES && (INTEG >= 2 || (NB_PHASED_AO && INTEG == 1))) {
+#if NB_TAIL_CUT
+            // suspended walks resume in every wave and do not vote on its kind (else a straggling shadow ray would
+            // hold the freshly regenerated camera rays back, wave after wave)
+            const bool carry = ps.stage != ST_IDLE && tr.node != kDone;
+            const bool any_shadow = __ballot_sync(0xffffffffu, !carry && ps.stage >= ST_SHADOW) != 0u;
+            traced = carry || (any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND));
+#else
             const bool any_shadow = __ballot_sync(0xffffffffu, ps.stage >= ST_SHADOW) != 0u;
             traced = (any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND));
-            if (NB_TAIL_CUT) traced = traced || (ps.stage != ST_IDLE && tr.node != kDone);
+#endif
         }
         if (traced) {
 #if NB_TAIL_CUT

@@ -1,0 +1,28 @@
+#!/bin/bash
+# Round-2 opening measurement (one gpurun call, ~4 GPU-minutes).  Build the variants HERE first:
+#   bash tools/round2_experiments.sh --build      (cross-compiles; no GPU needed)
+# then on the box:   gpurun --timeout 420 -- 'bash tools/round2_experiments.sh > gpurun_out/r2_exp.log 2>&1'
+# Variants (all default-off switches in nori_b200/csrc/nb_kernels.cuh):
+#   _compact : NB_COMPACT_PATH=1  -- tile rectangle re-derived at splat time (static spill bytes 650 -> 606 path, 222 -> 182 ao)
+#   _tail    : NB_TAIL_CUT=1      -- resumable walks; run time option "tail" (tools/tail_sweep.py sweeps it)
+#   _both    : both
+if [ "$1" = "--build" ]; then
+python - <<'PY'
+from nori_b200 import build
+build.build_cuda()
+build.build_cuda(force=True, variant="_compact", extra_flags=("-DNB_COMPACT_PATH=1",))
+build.build_cuda(force=True, variant="_tail", extra_flags=("-DNB_TAIL_CUT=1",))
+build.build_cuda(force=True, variant="_both", extra_flags=("-DNB_TAIL_CUT=1", "-DNB_COMPACT_PATH=1"))
+PY
+exit $?
+fi
+set -x
+bash tools/ab_variants.sh "default _compact default _compact" "ajax-ao cbox-mis"
+# a walk that never ends must not take the box with it: the earlier tail-cut build livelocked
+for lib in _tail _both; do
+  NORI_B200_LIB=nori_b200/lib/libnori_b200$lib.so TAILS="0 2 4 8 12" timeout 90 python tools/tail_sweep.py ajax-ao cbox-mis
+done
+# parity of the winning variants against the oracle
+for lib in _compact _tail; do
+  NORI_B200_LIB=nori_b200/lib/libnori_b200$lib.so timeout 120 python -m pytest tests/test_gpu_parity.py -q -x -k "film_parity" 2>&1 | tail -2
+done
