@@ -492,6 +492,7 @@ int nb_build_stats(nb_ctx *c, double *seconds, int *builder) {
 
 int nb_set_camera(nb_ctx *c, const float s2c[16], const float c2w[16], int width, int height, float nearClip, float farClip) {
     if (!c) return fail("null context");
+    if (!s2c || !c2w) return fail("nb_set_camera: null matrix");
     if (width <= 0 || height <= 0 || width > 32767 || height > 32767) return fail("invalid output size %dx%d", width, height);
     memcpy(c->s2c, s2c, sizeof c->s2c); memcpy(c->c2w, c2w, sizeof c->c2w);
     c->W = width; c->H = height; c->nearClip = nearClip; c->farClip = farClip; c->have_camera = true;
@@ -500,6 +501,7 @@ int nb_set_camera(nb_ctx *c, const float s2c[16], const float c2w[16], int width
 
 int nb_set_filter(nb_ctx *c, const float table[NB_FILTER_RESOLUTION + 1], float radius) {
     if (!c) return fail("null context");
+    if (!table) return fail("nb_set_filter: null table");
     if (!(radius > 0)) return fail("invalid filter radius %f", radius);
     int border = (int) std::ceil(radius - 0.5f);     // ref: src/block.cpp:20
     if (border > 8) return fail("filter radius %f too large", radius);
@@ -549,6 +551,8 @@ int nb_render_blocks_device(nb_ctx *c, float *blocks_dev, void *stream, nb_stats
 
 int nb_merge_blocks_device(nb_ctx *c, const float *blocks_dev, int rank, int nranks, float *film_dev, void *stream) {
     if (!c || !blocks_dev || !film_dev) return fail("null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("invalid tile shard (%d of %d)", rank, nranks);
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
     if (ensure_device(c)) return 1;
     cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
     int n = tiles_for(c, rank, nranks, nullptr, nullptr);
