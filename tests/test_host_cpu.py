@@ -137,3 +137,35 @@ def test_obj_binary_cache_round_trip(tmp_path):
     assert np.allclose(c["V"], 2 * a["V"], rtol=1e-6)
     d = host.HostScene(str(tmp_path / "a.xml")).mesh(0)
     assert np.array_equal(d["V"], a["V"])
+
+
+REF_SCENES = "/root/reference/scenes"
+# reference scene files this mirror does not load, and why (everything else under scenes/ must parse)
+REF_SCENE_GAPS = {
+    "pa2/ajax-normals.xml": "ajax.obj", "pa3/ajax-ao.xml": "ajax.obj", "pa5/ajax/ajax-rough.xml": "ajax.obj",
+    "pa5/ajax/ajax-smooth.xml": "ajax.obj",                       # mesh not shipped with the reference
+    "pa3/ajax-simple.xml": 'class "simple"',                      # point-light integrator: not built yet
+    "pa4/tests/test-mesh.xml": 'class "ttest"', "pa4/tests/test-mesh-furnace.xml": 'class "ttest"',
+    "pa5/tests/test-direct.xml": 'class "ttest"', "pa5/tests/test-furnace.xml": 'class "ttest"',
+    "pa5/tests/ttest-microfacet.xml": 'class "ttest"', "pa5/tests/chi2test-microfacet.xml": 'class "chi2test"',
+}                                                                  # test runners: restated in tests/fixtures.py instead
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="reference checkout not present (GPU box)")
+def test_every_shipped_reference_scene_loads():
+    """Scene-file coverage of the XML pipeline: all 25 files under the reference's scenes/ either load (plugins,
+    transforms, OBJ meshes, emitters resolved into C-ABI descriptors) or fail for the documented reason."""
+    import glob
+    seen = 0
+    for p in sorted(glob.glob(os.path.join(REF_SCENES, "**", "*.xml"), recursive=True)):
+        rel = os.path.relpath(p, REF_SCENES)
+        seen += 1
+        if rel in REF_SCENE_GAPS:
+            with pytest.raises(abi.NoriError, match=REF_SCENE_GAPS[rel].replace('"', '\\"')):
+                host.HostScene(p)
+            continue
+        h = host.HostScene(p)
+        info = h.info()
+        assert info["n_meshes"] >= 1 and info["n_triangles"] >= 2 and info["spp"] >= 1, rel
+        h.close()
+    assert seen == 25
