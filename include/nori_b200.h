@@ -34,7 +34,8 @@ enum { NB_BSDF_DIFFUSE = 0, NB_BSDF_MIRROR = 1, NB_BSDF_DIELECTRIC = 2, NB_BSDF_
 enum { NB_EMITTER_NONE = 0, NB_EMITTER_AREA = 1 };
 /* Integrator plugins named by the shipped scenes (ref: scenes/pa1/bunny.xml:8, pa3/ajax-ao.xml:8,
  * pa4/cbox/cbox-whitted.xml:4, pa5/cbox/cbox_{mats,ems,mis}.xml:4); interface ref: include/nori/integrator.h:42 */
-enum { NB_INT_NORMALS = 0, NB_INT_AO = 1, NB_INT_WHITTED = 2, NB_INT_PATH_MATS = 3, NB_INT_PATH_EMS = 4, NB_INT_PATH_MIS = 5 };
+enum { NB_INT_NORMALS = 0, NB_INT_AO = 1, NB_INT_WHITTED = 2, NB_INT_PATH_MATS = 3, NB_INT_PATH_EMS = 4, NB_INT_PATH_MIS = 5,
+       NB_INT_SIMPLE = 6 /* point light, needs nb_set_point_light (ref: scenes/pa3/ajax-simple.xml:8-11) */ };
 /* Sampler stream assignment.  PER_BLOCK is the reference's Independent::prepare (ref: src/independent.cpp:36-41):
  * one sequential pcg32 stream per 32x32 block.  PER_SAMPLE seeds one stream per (pixel, sample) through the
  * generate()/advance() hooks of the Sampler API (ref: include/nori/sampler.h:66-83) and is the parallel-friendly mode. */
@@ -117,6 +118,9 @@ int nb_set_sampler(nb_ctx *, uint32_t spp, int seed_mode, uint64_t seed);
 
 /* Integrator selection; unsupported type -> error (no CPU fallback). */
 int nb_set_integrator(nb_ctx *, const nb_integrator_desc *);
+/* Properties of the `simple` integrator (ref: scenes/pa3/ajax-simple.xml:9-10): <point name="position">, <color name="energy">.
+ * Li = energy / (4 pi^2) * max(0, cos theta) / |x - position|^2 * V(x <-> position).  Required before rendering NB_INT_SIMPLE. */
+int nb_set_point_light(nb_ctx *, const float position[3], const float energy[3]);
 
 /* Tile sharding across GPUs: this context renders only 32x32 tiles with tile_id % nranks == rank
  * (tile_id = by * ceil(W/32) + bx).  Default (0, 1) = all tiles.  Replaces BlockGenerator::next

@@ -75,6 +75,7 @@ def lib():
         L.nb_set_filter.argtypes = [vp, vp, f]
         L.nb_set_sampler.argtypes = [vp, u32, i, u64]
         L.nb_set_integrator.argtypes = [vp, C.POINTER(IntegratorDesc)]
+        L.nb_set_point_light.argtypes = [vp, vp, vp]
         L.nb_set_tiles.argtypes = [vp, i, i]
         L.nb_render.argtypes = [vp, vp, sp]
         L.nb_render_device.argtypes = [vp, vp, vp, sp]
@@ -166,6 +167,10 @@ class Context:
         _check(L.nb_set_sampler(self.h, scene.spp, scene.seed_mode, scene.seed))
         it = IntegratorDesc(int(scene.integrator), int(scene.rr_start), int(scene.max_depth), 0)
         _check(L.nb_set_integrator(self.h, C.byref(it)))
+        if getattr(scene, "light_pos", None) is not None:      # `simple` integrator only
+            lp = np.ascontiguousarray(scene.light_pos, dtype=np.float32)
+            le = np.ascontiguousarray(scene.light_energy, dtype=np.float32)
+            _check(L.nb_set_point_light(self.h, _p(lp), _p(le)))
 
     def build_stats(self):
         sec, b = C.c_double(), C.c_int()

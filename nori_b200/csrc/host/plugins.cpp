@@ -121,6 +121,26 @@ NORI_DEVICE_INTEGRATOR(PathMatsIntegrator, "path_mats"); // ref: scenes/pa5/cbox
 NORI_DEVICE_INTEGRATOR(PathEmsIntegrator, "path_ems");   // ref: scenes/pa5/cbox/cbox_ems.xml:4
 NORI_DEVICE_INTEGRATOR(PathMisIntegrator, "path_mis");   // ref: scenes/pa5/cbox/cbox_mis.xml:4
 
+/// Point-light integrator of ref: scenes/pa3/ajax-simple.xml:8-11.  Both properties are mandatory (a missing one
+/// throws from PropertyList, as any plugin constructor of the reference does); Li() runs on the device.
+class SimpleIntegrator : public Integrator {
+public:
+    SimpleIntegrator(const PropertyList &props) {
+        m_position = props.getPoint("position");
+        m_energy = props.getColor("energy");
+    }
+    Color3f Li(const Scene *, Sampler *, const Ray3f &) const {
+        throw NoriException("SimpleIntegrator::Li(): this integrator is evaluated by the CUDA render path (nb_render)");
+    }
+    std::string toString() const {
+        return format("SimpleIntegrator[\n  position = %s,\n  energy = %s\n]", m_position.toString(), m_energy.toString());
+    }
+private:
+    Point3f m_position;
+    Color3f m_energy;
+};
+NORI_REGISTER_CLASS(SimpleIntegrator, "simple");
+
 // ------------------------------------------------------------------ sampler
 /// Independent sampling (ref: src/independent.cpp:21-65).  "seedMode" = "sample" (default; one pcg32 stream per
 /// (pixel, sample), the parallel mode) or "block" (the reference's Independent::prepare: one stream per 32x32 block).

@@ -59,7 +59,7 @@ nb_integrator_desc describeIntegrator(const Integrator *integ) {
     const NoriObjectFactory::Record *rec = NoriObjectFactory::creationRecord(integ);
     if (!rec) throw NoriException("Integrator %s was not created through NoriObjectFactory", integ->toString());
     static const std::map<std::string, int> types = { { "normals", NB_INT_NORMALS }, { "ao", NB_INT_AO }, { "whitted", NB_INT_WHITTED },
-        { "path_mats", NB_INT_PATH_MATS }, { "path_ems", NB_INT_PATH_EMS }, { "path_mis", NB_INT_PATH_MIS } };
+        { "path_mats", NB_INT_PATH_MATS }, { "path_ems", NB_INT_PATH_EMS }, { "path_mis", NB_INT_PATH_MIS }, { "simple", NB_INT_SIMPLE } };
     auto it = types.find(rec->type);
     if (it == types.end()) throw NoriException("Integrator plugin \"%s\" has no device implementation (the GPU path has no CPU fallback)", rec->type);
     d.type = it->second;
@@ -97,6 +97,12 @@ nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const Rend
         if (nb_set_sampler(ctx, (uint32_t) scene->getSampler()->getSampleCount(), blockMode ? NB_SEED_PER_BLOCK : NB_SEED_PER_SAMPLE, seed)) throwLast("nb_set_sampler");
         nb_integrator_desc id = describeIntegrator(scene->getIntegrator());
         if (nb_set_integrator(ctx, &id)) throwLast("nb_set_integrator");
+        if (id.type == NB_INT_SIMPLE) {
+            const PropertyList &ip = NoriObjectFactory::creationRecord(scene->getIntegrator())->props;
+            const Point3f pos = ip.getPoint("position"); const Color3f en = ip.getColor("energy");
+            const float p3[3] = { pos.x(), pos.y(), pos.z() }, e3[3] = { en.r(), en.g(), en.b() };
+            if (nb_set_point_light(ctx, p3, e3)) throwLast("nb_set_point_light");
+        }
         if (nb_set_tiles(ctx, opt.tileRank, opt.tileRanks)) throwLast("nb_set_tiles");
     } catch (...) {
         nb_destroy(ctx);

@@ -70,6 +70,7 @@ struct nb_ctx {
     float ftable[33]; float fradius = 2.0f; int border = 2;
     uint32_t spp = 1; int seed_mode = NB_SEED_PER_SAMPLE; uint64_t seed = 0;
     nb_integrator_desc integ = { NB_INT_NORMALS, 3, 0, 0 };
+    float light_pos[3] = { 0, 0, 0 }, light_energy[3] = { 0, 0, 0 }; bool have_light = false;
     int tile_rank = 0, tile_nranks = 1;
     // work buffers
     float4 *blocks = nullptr; size_t blocks_cap = 0;
@@ -135,7 +136,9 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     nb::RenderParams P;
     memset(&P, 0, sizeof P);
     if (fill_scene(c, P.sc)) return 1;
-    if (c->integ.type < NB_INT_NORMALS || c->integ.type > NB_INT_PATH_MIS) return fail("unsupported integrator type %d (no CPU fallback)", c->integ.type);
+    if (c->integ.type < NB_INT_NORMALS || c->integ.type > NB_INT_SIMPLE) return fail("unsupported integrator type %d (no CPU fallback)", c->integ.type);
+    if (c->integ.type == NB_INT_SIMPLE && !c->have_light) return fail("the simple integrator needs nb_set_point_light");
+    memcpy(P.light_pos, c->light_pos, sizeof P.light_pos); memcpy(P.light_energy, c->light_energy, sizeof P.light_energy);
     memcpy(P.s2c, c->s2c, sizeof P.s2c); memcpy(P.c2w, c->c2w, sizeof P.c2w);
     P.W = c->W; P.H = c->H; P.invW = 1.0f / (float) c->W; P.invH = 1.0f / (float) c->H;   // cwiseInverse, ref: src/perspective.cpp:27
     P.nearClip = c->nearClip; P.farClip = c->farClip;
@@ -187,7 +190,8 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     switch (c->integ.type) {
         case 0: oe = occupancy<0>(&occ, count, P.smem_nodes > 0, smem); break; case 1: oe = occupancy<1>(&occ, count, P.smem_nodes > 0, smem); break;
         case 2: oe = occupancy<2>(&occ, count, P.smem_nodes > 0, smem); break; case 3: oe = occupancy<3>(&occ, count, P.smem_nodes > 0, smem); break;
-        case 4: oe = occupancy<4>(&occ, count, P.smem_nodes > 0, smem); break; default: oe = occupancy<5>(&occ, count, P.smem_nodes > 0, smem); break;
+        case 4: oe = occupancy<4>(&occ, count, P.smem_nodes > 0, smem); break; case 5: oe = occupancy<5>(&occ, count, P.smem_nodes > 0, smem); break;
+        default: oe = occupancy<6>(&occ, count, P.smem_nodes > 0, smem); break;
     }
     if (oe != cudaSuccess) return fail("occupancy query failed: %s", cudaGetErrorString(oe));
     if (occ < 1) return fail("render kernel does not fit on an SM (smem %zu B)", smem);
@@ -205,7 +209,8 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
             case 2: launch_render<2>(P, count, block_mode, grid, smem, s); break;
             case 3: launch_render<3>(P, count, block_mode, grid, smem, s); break;
             case 4: launch_render<4>(P, count, block_mode, grid, smem, s); break;
-            default: launch_render<5>(P, count, block_mode, grid, smem, s); break;
+            case 5: launch_render<5>(P, count, block_mode, grid, smem, s); break;
+            default: launch_render<6>(P, count, block_mode, grid, smem, s); break;
         }
         CK(cudaGetLastError());
     }
@@ -520,8 +525,15 @@ int nb_set_sampler(nb_ctx *c, uint32_t spp, int seed_mode, uint64_t seed) {
 
 int nb_set_integrator(nb_ctx *c, const nb_integrator_desc *d) {
     if (!c || !d) return fail("null argument");
-    if (d->type < NB_INT_NORMALS || d->type > NB_INT_PATH_MIS) return fail("unsupported integrator type %d (no CPU fallback)", d->type);
+    if (d->type < NB_INT_NORMALS || d->type > NB_INT_SIMPLE) return fail("unsupported integrator type %d (no CPU fallback)", d->type);
     c->integ = *d;
+    return 0;
+}
+
+int nb_set_point_light(nb_ctx *c, const float position[3], const float energy[3]) {
+    if (!c || !position || !energy) return fail("null argument");
+    memcpy(c->light_pos, position, sizeof c->light_pos); memcpy(c->light_energy, energy, sizeof c->light_energy);
+    c->have_light = true;
     return 0;
 }
 

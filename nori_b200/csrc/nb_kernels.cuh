@@ -90,6 +90,7 @@ struct RenderParams {
     int32_t smem_nodes;             // nodes staged in shared memory (0 = none)
     int32_t block_stream_skip;      // per-block seeding served by skip-ahead (fixed draws per sample)
     int32_t tail_lanes;             // a wave's walk is suspended once <= tail_lanes lanes are still walking (0 = never)
+    float light_pos[3], light_energy[3];   // point light of the `simple` integrator (appended: older fields keep their offsets)
 };
 
 // ------------------------------------------------------------------ traversal state (per lane)
@@ -459,6 +460,21 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
         ps.stage = ST_SHADOW_AO;
         return false;
     }
+    if (INTEG == 6) {                                   // simple: one point light (oracle.c: ORC_INT_SIMPLE, same operation order)
+        const V3 dvec = mk(P.light_pos[0], P.light_pos[1], P.light_pos[2]) - its.p;
+        const float dist2 = dot(dvec, dvec);
+        const float dist = sqrtf(dist2);
+        const V3 wo_w = mk(dvec.x / dist, dvec.y / dist, dvec.z / dist);
+        const float cosT = dot(its.sh.n, wo_w);
+        if (!(cosT > 0.0f)) return true;
+        const float g = cosT / dist2 * 0.025330295910584444f;      // 1 / (4 pi^2)
+        ps.contrib = mk(P.light_energy[0] * g, P.light_energy[1] * g, P.light_energy[2] * g);
+        ps.has_next = false;
+        ray.ox = its.p.x; ray.oy = its.p.y; ray.oz = its.p.z; ray.dx = wo_w.x; ray.dy = wo_w.y; ray.dz = wo_w.z;
+        ray.mint = NB_EPSILON; ray.maxt = dist - NB_EPSILON;
+        ps.stage = ST_SHADOW;                           // resolved by the ST_SHADOW branch above: L += contrib if unoccluded
+        return false;
+    }
     const DevMesh &m = sc.meshes[its.mesh];
     const V3 wi = to_local(its.sh, neg(mk(ray.dx, ray.dy, ray.dz)));
     const bool diffuse = bsdf_is_diffuse(m);
@@ -599,7 +615,7 @@ __device__ __forceinline__ void tma_stage_nodes(float4 *snodes, const float4 *gn
 
 // ------------------------------------------------------------------ the fused persistent kernel (K1..K5)
 template <int INTEG, bool COUNT, bool TMA_TOP>
-__global__ void __launch_bounds__(128, (INTEG <= 1) ? NB_MIN_BLOCKS : NB_MIN_BLOCKS_PATH) render_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCKS : NB_MIN_BLOCKS_PATH) render_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *snodes = reinterpret_cast<float4 *>(smem_raw);
     __shared__ __align__(8) uint64_t mbar;

@@ -12,14 +12,14 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass, field
-from typing import List, Optional
+from typing import List, Optional, Sequence
 
 import numpy as np
 
 BSDF_DIFFUSE, BSDF_MIRROR, BSDF_DIELECTRIC, BSDF_MICROFACET = 0, 1, 2, 3
-INT_NORMALS, INT_AO, INT_WHITTED, INT_PATH_MATS, INT_PATH_EMS, INT_PATH_MIS = range(6)
+INT_NORMALS, INT_AO, INT_WHITTED, INT_PATH_MATS, INT_PATH_EMS, INT_PATH_MIS, INT_SIMPLE = range(7)
 INTEGRATORS = {"normals": INT_NORMALS, "ao": INT_AO, "whitted": INT_WHITTED,
-               "path_mats": INT_PATH_MATS, "path_ems": INT_PATH_EMS, "path_mis": INT_PATH_MIS}
+               "path_mats": INT_PATH_MATS, "path_ems": INT_PATH_EMS, "path_mis": INT_PATH_MIS, "simple": INT_SIMPLE}
 SEED_PER_SAMPLE, SEED_PER_BLOCK = 0, 1
 BLOCK = 32
 FILTER_RES = 32
@@ -105,6 +105,8 @@ class Scene:
     rr_start: int = 3
     max_depth: int = 0
     name: str = ""
+    light_pos: Optional[Sequence[float]] = None      # point light of the `simple` integrator (position, energy)
+    light_energy: Optional[Sequence[float]] = None
 
     def __post_init__(self):
         if self.filter_table is None:

@@ -28,6 +28,7 @@
 #define ORC_EPSILON   1e-4f                    /* ref: include/nori/common.h:38 */
 #define ORC_PI        3.14159265358979323846f  /* ref: include/nori/common.h:43 */
 #define ORC_INV_PI    0.31830988618379067154f  /* ref: include/nori/common.h:44 */
+#define ORC_INV_FOURPI2 0.025330295910584444f  /* 1 / (4 pi^2) */
 #define ORC_BLOCK     32                       /* ref: include/nori/block.h:17 */
 #define ORC_FILTER_RES 32                      /* ref: include/nori/rfilter.h:12 */
 #define ORC_MISS      0xffffffffu
@@ -403,6 +404,7 @@ struct orc_scene {
     float ftable[ORC_FILTER_RES + 1]; float fradius; int border; float lookup;
     uint32_t spp; int seed_mode; uint64_t seed;
     orc_integrator integ;
+    float light_pos[3], light_energy[3];   /* point light of the `simple` integrator (scenes/pa3/ajax-simple.xml:8-11) */
     int tile_rank, tile_nranks;
 };
 
@@ -450,6 +452,9 @@ void orc_scene_set_filter(orc_scene *s, const float table[33], float radius) {
 }
 void orc_scene_set_sampler(orc_scene *s, uint32_t spp, int seed_mode, uint64_t seed) { s->spp = spp; s->seed_mode = seed_mode; s->seed = seed; }
 void orc_scene_set_integrator(orc_scene *s, const orc_integrator *i) { s->integ = *i; if (s->integ.rr_start <= 0) s->integ.rr_start = 3; }
+void orc_scene_set_point_light(orc_scene *s, const float position[3], const float energy[3]) {
+    memcpy(s->light_pos, position, sizeof s->light_pos); memcpy(s->light_energy, energy, sizeof s->light_energy);
+}
 void orc_scene_set_tiles(orc_scene *s, int rank, int nranks) { s->tile_rank = rank; s->tile_nranks = nranks < 1 ? 1 : nranks; }
 
 static inline void tri_verts(const mesh_t *m, uint32_t f, v3 *p0, v3 *p1, v3 *p2) {
@@ -887,6 +892,25 @@ static v3 Li(const orc_scene *s, orc_pcg32 *rng, ray_t ray, int accel, counters 
             ray_t sr; sr.o = its.p; sr.d = w; sr.mint = ORC_EPSILON; sr.maxt = INFINITY; ray_update(&sr);
             hit_t sh;
             if (!scene_search(s, &sr, 1, accel, &sh, c)) L = v3make(1, 1, 1);
+            break;
+        }
+
+        if (type == ORC_INT_SIMPLE) {
+            /* [authored] the course's point-light integrator named by scenes/pa3/ajax-simple.xml:8-11 (no source in the
+             * reference): Li = Phi / (4 pi^2) * max(0, cos theta) / |x - p|^2 * V(x <-> p); theta is measured against
+             * the shading normal; no sampler draws beyond the camera sample. */
+            v3 dvec = v3sub(ld3(s->light_pos), its.p);
+            float dist2 = dot3(dvec, dvec);
+            float dist = sqrtf(dist2);
+            v3 wo_w = v3make(dvec.x / dist, dvec.y / dist, dvec.z / dist);
+            float cosT = dot3(its.sh.n, wo_w);
+            if (cosT > 0.0f) {
+                float g = cosT / dist2 * ORC_INV_FOURPI2;
+                ray_t sr; sr.o = its.p; sr.d = wo_w; sr.mint = ORC_EPSILON; sr.maxt = dist - ORC_EPSILON; ray_update(&sr);
+                hit_t sh;
+                if (!scene_search(s, &sr, 1, accel, &sh, c))
+                    L = v3make(s->light_energy[0] * g, s->light_energy[1] * g, s->light_energy[2] * g);
+            }
             break;
         }
 

@@ -34,7 +34,7 @@ extern "C" {
 enum { ORC_BSDF_DIFFUSE = 0, ORC_BSDF_MIRROR = 1, ORC_BSDF_DIELECTRIC = 2, ORC_BSDF_MICROFACET = 3 };
 enum { ORC_EMITTER_NONE = 0, ORC_EMITTER_AREA = 1 };
 enum { ORC_INT_NORMALS = 0, ORC_INT_AO = 1, ORC_INT_WHITTED = 2,
-       ORC_INT_PATH_MATS = 3, ORC_INT_PATH_EMS = 4, ORC_INT_PATH_MIS = 5 };
+       ORC_INT_PATH_MATS = 3, ORC_INT_PATH_EMS = 4, ORC_INT_PATH_MIS = 5, ORC_INT_SIMPLE = 6 };
 enum { ORC_SEED_PER_SAMPLE = 0, ORC_SEED_PER_BLOCK = 1 };
 enum { ORC_ACCEL_BRUTE = 0, ORC_ACCEL_BVH = 1 };
 
@@ -82,6 +82,7 @@ void orc_scene_set_camera(orc_scene *, const float s2c[16], const float c2w[16],
 void orc_scene_set_filter(orc_scene *, const float table[33], float radius);
 void orc_scene_set_sampler(orc_scene *, uint32_t spp, int seed_mode, uint64_t seed);
 void orc_scene_set_integrator(orc_scene *, const orc_integrator *);
+void orc_scene_set_point_light(orc_scene *, const float position[3], const float energy[3]);  /* `simple` integrator */
 void orc_scene_set_tiles(orc_scene *, int rank, int nranks);  /* render only tiles with id % nranks == rank */
 
 /* ---- the path ---- */

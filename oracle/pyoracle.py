@@ -66,6 +66,7 @@ def lib():
         L.orc_scene_set_filter.argtypes = [vp, vp, C.c_float]
         L.orc_scene_set_sampler.argtypes = [vp, C.c_uint32, C.c_int, C.c_uint64]
         L.orc_scene_set_integrator.argtypes = [vp, C.POINTER(Integrator)]
+        L.orc_scene_set_point_light.argtypes = [vp, vp, vp]
         L.orc_scene_set_tiles.argtypes = [vp, C.c_int, C.c_int]
         L.orc_render.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(Stats)]
         L.orc_intersect.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.POINTER(Stats)]
@@ -142,6 +143,10 @@ class OracleScene:
         L.orc_scene_set_sampler(self.h, scene.spp, scene.seed_mode, scene.seed)
         it = Integrator(int(scene.integrator), int(scene.rr_start), int(scene.max_depth), 0)
         L.orc_scene_set_integrator(self.h, C.byref(it))
+        if getattr(scene, "light_pos", None) is not None:
+            lp = np.ascontiguousarray(scene.light_pos, dtype=np.float32)
+            le = np.ascontiguousarray(scene.light_energy, dtype=np.float32)
+            L.orc_scene_set_point_light(self.h, _p(lp), _p(le))
 
     def close(self):
         if self.h:

@@ -12,7 +12,7 @@ from nori_b200 import scene as S
 
 def test_every_hot_path_plugin_is_registered():
     names = ["scene", "obj", "diffuse", "mirror", "dielectric", "microfacet", "area", "independent", "perspective",
-             "gaussian", "mitchell", "tent", "box", "normals", "ao", "whitted", "path_mats", "path_ems", "path_mis"]
+             "gaussian", "mitchell", "tent", "box", "normals", "ao", "whitted", "path_mats", "path_ems", "path_mis", "simple"]
     assert all(host.is_registered(n) for n in names)
     assert not host.is_registered("photonmapper")
 
@@ -143,8 +143,7 @@ REF_SCENES = "/root/reference/scenes"
 # reference scene files this mirror does not load, and why (everything else under scenes/ must parse)
 REF_SCENE_GAPS = {
     "pa2/ajax-normals.xml": "ajax.obj", "pa3/ajax-ao.xml": "ajax.obj", "pa5/ajax/ajax-rough.xml": "ajax.obj",
-    "pa5/ajax/ajax-smooth.xml": "ajax.obj",                       # mesh not shipped with the reference
-    "pa3/ajax-simple.xml": 'class "simple"',                      # point-light integrator: not built yet
+    "pa5/ajax/ajax-smooth.xml": "ajax.obj", "pa3/ajax-simple.xml": "ajax.obj",   # mesh not shipped with the reference
     "pa4/tests/test-mesh.xml": 'class "ttest"', "pa4/tests/test-mesh-furnace.xml": 'class "ttest"',
     "pa5/tests/test-direct.xml": 'class "ttest"', "pa5/tests/test-furnace.xml": 'class "ttest"',
     "pa5/tests/ttest-microfacet.xml": 'class "ttest"', "pa5/tests/chi2test-microfacet.xml": 'class "chi2test"',
@@ -169,3 +168,20 @@ def test_every_shipped_reference_scene_loads():
         assert info["n_meshes"] >= 1 and info["n_triangles"] >= 2 and info["spp"] >= 1, rel
         h.close()
     assert seen == 25
+
+
+def test_simple_integrator_xml(tmp_path):
+    """ref: scenes/pa3/ajax-simple.xml:8-11 -- `simple` takes a point and a colour; both are mandatory."""
+    obj = tmp_path / "tri.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    body = '<mesh type="obj"><string name="filename" value="tri.obj"/></mesh><camera type="perspective"/>'
+    ok = tmp_path / "ok.xml"
+    ok.write_text('<scene><integrator type="simple"><point name="position" value="-20, 40, 20"/>'
+                  '<color name="energy" value="3.76e4, 3.76e4, 3.76e4"/></integrator>' + body + '</scene>')
+    h = host.HostScene(ok)
+    assert h.info()["integrator"] == S.INT_SIMPLE
+    h.close()
+    bad = tmp_path / "bad.xml"
+    bad.write_text('<scene><integrator type="simple"><point name="position" value="0,0,0"/></integrator>' + body + '</scene>')
+    with pytest.raises(abi.NoriError, match="energy"):
+        host.HostScene(bad)
