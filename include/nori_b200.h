@@ -122,6 +122,13 @@ int nb_set_integrator(nb_ctx *, const nb_integrator_desc *);
  * Li = energy / (4 pi^2) * max(0, cos theta) / |x - position|^2 * V(x <-> position).  Required before rendering NB_INT_SIMPLE. */
 int nb_set_point_light(nb_ctx *, const float position[3], const float energy[3]);
 
+/* Li of n independent camera paths over the whole image plane -- the loop of the reference's t-test in scene mode
+ * (ref: src/ttest.cpp:153-167): pixelSample = next2D() * outputSize, apertureSample = next2D(), value = Li(ray);
+ * lum_host[k] receives value.getLuminance() (ref: src/common.cpp:206-208) of path k.  The reference consumes one
+ * sequential sampler stream across all paths; here path k owns the pcg32 stream seed((seed << 32) + k, 0), seed being
+ * the one given to nb_set_sampler.  Needs scene, camera and integrator; film, filter and tiling are not used. */
+int nb_li_samples(nb_ctx *, uint64_t n, float *lum_host, nb_stats *stats /* nullable */);
+
 /* Tile sharding across GPUs: this context renders only 32x32 tiles with tile_id % nranks == rank
  * (tile_id = by * ceil(W/32) + bx).  Default (0, 1) = all tiles.  Replaces BlockGenerator::next
  * as the work scheduler (ref: src/block.cpp:119-152). */

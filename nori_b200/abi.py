@@ -83,6 +83,7 @@ def lib():
         L.nb_tile_count.argtypes = [vp, i, i, C.POINTER(i), C.POINTER(i)]
         L.nb_merge_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
         L.nb_merge_all_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
+        L.nb_li_samples.argtypes = [vp, u64, vp, sp]
         L.nb_intersect.argtypes = [vp, vp, u64, vp, i, sp]
         L.nb_intersect_device.argtypes = [vp, vp, u64, vp, i, vp, sp]
         L.nb_intersect_full.argtypes = [vp, vp, u64, vp]
@@ -231,6 +232,13 @@ class Context:
 
     def merge_all_blocks_device(self, blocks_ptr: int, nranks: int, stride_tiles: int, film_ptr: int, stream: int = 0):
         _check(lib().nb_merge_all_blocks_device(self.h, C.c_void_p(blocks_ptr), nranks, stride_tiles, C.c_void_p(film_ptr), C.c_void_p(stream)))
+
+    def li_samples(self, n: int):
+        """nb_li_samples: luminance of Li for n independent camera paths (t-test scene mode, ref: src/ttest.cpp:153-167)."""
+        lum = np.zeros(n, dtype=np.float32)
+        st = Stats()
+        _check(lib().nb_li_samples(self.h, n, _p(lum), C.byref(st)))
+        return lum, st
 
     def intersect(self, rays: np.ndarray, shadow=False):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

@@ -102,7 +102,11 @@ private:
             char q = s[pos++];
             size_t e = s.find(q, pos);
             if (e == std::string::npos) fail("unterminated attribute value");
-            n->attrs.emplace_back(k, unescape(s.substr(pos, e - pos)));
+            // attribute-value normalisation (XML 1.0 section 3.3.3): literal tab / CR / LF become spaces, so that a
+            // list written over several lines (ref: scenes/pa5/tests/test-direct.xml:4-7) tokenises on ", "
+            std::string raw = s.substr(pos, e - pos);
+            for (char &ch : raw) if (ch == '\t' || ch == '\n' || ch == '\r') ch = ' ';
+            n->attrs.emplace_back(k, unescape(raw));
             pos = e + 1;
         }
         for (;;) {   // children

@@ -620,6 +620,56 @@ int nb_render(nb_ctx *c, float *film_host, nb_stats *st) {
     return 0;
 }
 
+int nb_li_samples(nb_ctx *c, uint64_t n, float *lum_host, nb_stats *st) {
+    if (!c || (n && !lum_host)) return fail("null argument");
+    if (ensure_device(c)) return 1;
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    if (c->integ.type < NB_INT_NORMALS || c->integ.type > NB_INT_SIMPLE) return fail("unsupported integrator type %d (no CPU fallback)", c->integ.type);
+    if (c->integ.type == NB_INT_SIMPLE && !c->have_light) return fail("the simple integrator needs nb_set_point_light");
+    if (n > 0xffffffffULL) return fail("nb_li_samples: at most 2^32 - 1 paths");
+    nb::RenderParams P;
+    memset(&P, 0, sizeof P);
+    if (fill_scene(c, P.sc)) return 1;
+    memcpy(P.light_pos, c->light_pos, sizeof P.light_pos); memcpy(P.light_energy, c->light_energy, sizeof P.light_energy);
+    memcpy(P.s2c, c->s2c, sizeof P.s2c); memcpy(P.c2w, c->c2w, sizeof P.c2w);
+    P.W = c->W; P.H = c->H; P.invW = 1.0f / (float) c->W; P.invH = 1.0f / (float) c->H;
+    P.nearClip = c->nearClip; P.farClip = c->farClip;
+    P.seed = c->seed;
+    P.integrator = c->integ.type; P.rr_start = c->integ.rr_start > 0 ? c->integ.rr_start : 3;
+    P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
+    P.counters = c->counters;
+    if (st) memset(st, 0, sizeof *st);
+    if (n == 0) return 0;
+    cudaStream_t s = c->stream;
+    float *dl = nullptr;
+    CK(cudaMalloc(&dl, sizeof(float) * n));
+    int rc = 0;
+    const int grid = (int) std::min<uint64_t>((n + 127) / 128, (uint64_t) c->sm_count * 16);
+    cudaError_t e = cudaEventRecord(c->ev[0], s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev[1], s);
+    if (e == cudaSuccess) {
+        switch (c->integ.type) {
+            case 0: nb::li_samples_kernel<0><<<grid, 128, 0, s>>>(P, n, dl); break;
+            case 1: nb::li_samples_kernel<1><<<grid, 128, 0, s>>>(P, n, dl); break;
+            case 2: nb::li_samples_kernel<2><<<grid, 128, 0, s>>>(P, n, dl); break;
+            case 3: nb::li_samples_kernel<3><<<grid, 128, 0, s>>>(P, n, dl); break;
+            case 4: nb::li_samples_kernel<4><<<grid, 128, 0, s>>>(P, n, dl); break;
+            case 5: nb::li_samples_kernel<5><<<grid, 128, 0, s>>>(P, n, dl); break;
+            default: nb::li_samples_kernel<6><<<grid, 128, 0, s>>>(P, n, dl); break;
+        }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev[2], s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lum_host, dl, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) rc = fail("nb_li_samples failed: %s", cudaGetErrorString(e));
+    if (!rc) rc = finish_stats(c, s, st, 0);
+    else cudaStreamSynchronize(s);
+    cudaFree(dl);
+    if (!rc && st) { st->samples = n; st->launches = 1; st->d2h_bytes = sizeof(float) * n; st->h2d_bytes = sizeof(nb::RenderParams); }
+    return rc;
+}
+
 int nb_intersect_device(nb_ctx *c, const nb_ray *rays_dev, uint64_t n, nb_hit *hits_dev, int shadow, void *stream, nb_stats *st) {
     if (!c) return fail("null context");
     if (ensure_device(c)) return 1;

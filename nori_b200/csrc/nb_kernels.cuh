@@ -783,6 +783,37 @@ __global__ void __launch_bounds__(32) render_block_mode_kernel(const __grid_cons
     atomicAdd(&P.counters[4], (unsigned long long) n_hits);
 }
 
+// Li of n independent camera paths, the device counterpart of the loop of the reference's t-test in scene mode
+// (ref: src/ttest.cpp:153-167): pixelSample = next2D() * outputSize, apertureSample = next2D(), value = Li, and the
+// luminance of value (ref: src/common.cpp:206-208) is what the test accumulates.  The reference walks ONE sequential
+// sampler stream through all paths, which cannot be split; here path k owns the stream seed((seed << 32) + k, 0)
+// (oracle.c: orc_li_samples).  One thread per path: a test utility, not a throughput path.
+template <int INTEG>
+__global__ void __launch_bounds__(128) li_samples_kernel(const __grid_constant__ RenderParams P, unsigned long long n, float *lum) {
+    int stack[kStack];
+    Path ps; Ray ray; Trav tr;
+    unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
+    for (unsigned long long k = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long) gridDim.x * blockDim.x) {
+        pcg_seed(ps.rng, (P.seed << 32) + k, 0ull);
+        ps.sx = pcg_next_float(ps.rng) * (float) P.W;
+        ps.sy = pcg_next_float(ps.rng) * (float) P.H;
+        pcg_next_float(ps.rng); pcg_next_float(ps.rng);
+        sample_ray(P, ps.sx, ps.sy, ray);
+        ps.L = mk(0, 0, 0); ps.T = mk(1, 1, 1);
+        ps.depth = 0; ps.prev_specular = true; ps.prev_pdf = 0.0f; ps.has_next = false;
+        ps.stage = ST_EXTEND;
+        for (;;) {
+            trav_begin(ray, tr); n_rays++;
+            trav_run<false, false>(P.sc, nullptr, 0, ray, tr, stack, ps.stage != ST_EXTEND, n_nodes, n_tris);
+            if (shade<INTEG>(P, ps, ray, tr, n_hits)) break;
+        }
+        lum[k] = ps.L.x * 0.212671f + ps.L.y * 0.715160f + ps.L.z * 0.072169f;
+    }
+    atomicAdd(&P.counters[1], (unsigned long long) n_rays);
+    atomicAdd(&P.counters[4], (unsigned long long) n_hits);
+}
+
 // ------------------------------------------------------------------ K6: merge finished blocks into the full film (ref: src/block.cpp:93-102)
 __global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank, int nranks, int ntx, int W, int H,
                                     int border, int block_edge, float4 *film) {

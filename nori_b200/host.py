@@ -120,7 +120,12 @@ def _f(x):
 def write_xml(scene: S.Scene, directory: str, name: str = "scene", filter_xml: str | None = None) -> str:
     """Writes <directory>/<name>.xml plus one OBJ per mesh, in the reference's scene grammar (ref: src/parser.cpp:78-102)."""
     os.makedirs(directory, exist_ok=True)
-    lines = ["<?xml version='1.0' encoding='utf-8'?>", "<scene>", f'\t<integrator type="{_INT_XML[scene.integrator]}"/>',
+    if scene.integrator == S.INT_SIMPLE:
+        integ = ['\t<integrator type="simple">', '\t\t<point name="position" value="' + ", ".join(_f(v) for v in scene.light_pos) + '"/>',
+                 '\t\t<color name="energy" value="' + ", ".join(_f(v) for v in scene.light_energy) + '"/>', "\t</integrator>"]
+    else:
+        integ = [f'\t<integrator type="{_INT_XML[scene.integrator]}"/>']
+    lines = ["<?xml version='1.0' encoding='utf-8'?>", "<scene>"] + integ + [
              '\t<sampler type="independent">', f'\t\t<integer name="sampleCount" value="{scene.spp}"/>',
              f'\t\t<string name="seedMode" value="{"block" if scene.seed_mode == S.SEED_PER_BLOCK else "sample"}"/>', "\t</sampler>"]
     cam = scene.camera

@@ -1130,6 +1130,21 @@ int orc_ttest_scene(orc_scene *s, uint64_t n, int accel, double *lum) {
     return 0;
 }
 
+/* The same loop with one pcg32 stream PER PATH (path k: seed((seed << 32) + k, 0)) -- the parallel form that
+ * nb_li_samples evaluates on the device; lum is fp32 and must match it bit for bit. */
+int orc_li_samples(orc_scene *s, uint64_t n, int accel, float *lum) {
+    counters c = { 0, 0, 0 };
+    for (uint64_t k = 0; k < n; ++k) {
+        orc_pcg32 rng; orc_pcg32_seed(&rng, (s->seed << 32) + k, 0);
+        float sx = orc_pcg32_next_float(&rng) * (float) s->W, sy = orc_pcg32_next_float(&rng) * (float) s->H;
+        orc_pcg32_next_float(&rng); orc_pcg32_next_float(&rng);
+        ray_t ray; sample_ray(s, sx, sy, &ray);
+        v3 v = Li(s, &rng, ray, accel, &c);
+        lum[k] = v.x * 0.212671f + v.y * 0.715160f + v.z * 0.072169f;
+    }
+    return 0;
+}
+
 /* BSDF-mode t-test sampling: ref src/ttest.cpp:104-125 (wi = sphericalDirection(angle, 0), ref src/common.cpp:224-236).
  * The caller owns the rng so that consecutive angles continue ONE stream, as the reference does. */
 int orc_bsdf_sample_batch(const orc_bsdf *b, const float wi_[3], uint64_t n, orc_pcg32 *rng, float *wo_out, float *weight_out) {

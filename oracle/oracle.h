@@ -95,6 +95,8 @@ int  orc_intersect_full(orc_scene *, const orc_ray *, uint64_t n, float *out16, 
 /* Li of n camera paths the way ttest scene mode draws them (src/ttest.cpp:153-167): one sequential
  * default-constructed... see oracle.c.  lum[n] receives the luminance of each path. */
 int  orc_ttest_scene(orc_scene *, uint64_t n, int accel_kind, double *lum);
+/* the same loop with one stream per path (path k: seed((seed << 32) + k, 0)): the oracle of nb_li_samples */
+int  orc_li_samples(orc_scene *, uint64_t n, int accel_kind, float *lum);
 int  orc_film_to_rgb(const float *film, int W, int H, int border, float *rgb);  /* toBitmap, src/block.cpp:45-51 */
 int  orc_block_order(int W, int H, int block, int32_t *xy);  /* BlockGenerator spiral (src/block.cpp:109-152); returns count */
 

@@ -72,6 +72,7 @@ def lib():
         L.orc_intersect.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.POINTER(Stats)]
         L.orc_intersect_full.argtypes = [vp, vp, C.c_uint64, vp, C.c_int]
         L.orc_ttest_scene.argtypes = [vp, C.c_uint64, C.c_int, vp]
+        L.orc_li_samples.argtypes = [vp, C.c_uint64, C.c_int, vp]
         L.orc_film_to_rgb.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
         L.orc_block_order.argtypes = [C.c_int, C.c_int, C.c_int, vp]
         L.orc_pcg32_init.argtypes = [C.POINTER(Pcg32)]
@@ -185,6 +186,11 @@ class OracleScene:
     def ttest_lum(self, n, accel=1):
         lum = np.zeros(n, dtype=np.float64)
         lib().orc_ttest_scene(self.h, n, accel, _p(lum))
+        return lum
+
+    def li_samples(self, n, accel=1):
+        lum = np.zeros(n, dtype=np.float32)
+        lib().orc_li_samples(self.h, n, accel, _p(lum))
         return lum
 
     def sample_ray(self, sx, sy):
