@@ -34,6 +34,17 @@ def golden_films():
     return out
 
 
+def golden_extras():
+    """Vectors of the entry points added late in round 1 (kept in their own file so that oracle_vectors.npz and the
+    GPU test that was validated against it stay untouched): a `simple` film and per-path luminances (li_samples)."""
+    cam = S.Camera(S.lookat(**S._AJAX_CAM).astype(np.float32), 30.0, 48, 36)
+    simple = S.Scene([S.ajax_standin(1)], cam, S.INT_SIMPLE, 2, name="golden-simple",
+                     light_pos=(-20.0, 40.0, 20.0), light_energy=(3.76e4, 3.76e4, 3.76e4))
+    li = golden_films()["path_mis"]
+    li.seed = 5
+    return simple, li
+
+
 if __name__ == "__main__":
     sc, rays = golden_rays()
     o = po.OracleScene(sc)
@@ -46,3 +57,8 @@ if __name__ == "__main__":
         data["rays_" + name] = np.array([st.rays], dtype=np.uint64)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_vectors.npz"), **data)
     print({k: v.shape for k, v in data.items()})
+    simple, li = golden_extras()
+    film, st = po.OracleScene(simple).render(accel=1, nthreads=1)
+    extra = {"film_simple": film, "rays_simple": np.array([st.rays], dtype=np.uint64), "li_path_mis": po.OracleScene(li).li_samples(4096)}
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_vectors_extra.npz"), **extra)
+    print({k: v.shape for k, v in extra.items()})

@@ -94,3 +94,17 @@ def test_ttest_object_through_cli(tmp_path):
     wrong = list(FX.POLYLUM_REFS); wrong[2] *= 1.2
     bad = subprocess.run([host.CLI_PATH, test_file("bad.xml", wrong)], capture_output=True, text=True, timeout=600)
     assert bad.returncode != 0 and "Passed 4/5 tests." in bad.stdout and "Some tests failed" in bad.stderr
+
+
+def test_cuda_path_reproduces_golden_extras():
+    import os as _os
+    from tests.golden.make_oracle_vectors import golden_extras
+    Z = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "oracle_vectors_extra.npz"))
+    simple, li = golden_extras()
+    with abi.Context(0) as ctx:
+        ctx.load(simple)
+        film, st = ctx.render()
+        assert st.rays == int(Z["rays_simple"][0]) and S.rel_l2(film, Z["film_simple"]) < 1e-5
+        ctx.load(li)
+        lum, _ = ctx.li_samples(4096)
+        assert lum.tobytes() == Z["li_path_mis"].tobytes()
