@@ -174,6 +174,12 @@ int nb_set_option(nb_ctx *, const char *key, int64_t value);
 /* Raw device counters of the last call (diagnostics; meaningful with option "count" = 1): [1] rays, [2] node visits,
  * [3] triangle tests, [4] hits shaded, [5] sum over lock-step waves of the LONGEST walk in the warp, [6] waves. */
 int nb_debug_counters(nb_ctx *, uint64_t out[8]);
+/* Host-only diagnostic (no context, no GPU): runs the SAH builder that nb_build_accel uses on verts4 (xyz + pad per vertex)
+ * / faces4 (i0, i1, i2, mesh per triangle) and returns the device layout -- 16 floats per node, 12 floats per leaf-ordered
+ * triangle (nori_b200/csrc/nb_bvh.h).  info = { nodes, leaf triangles, breadth-first top nodes, depth }.  Call with null
+ * outputs to size the arrays (capacities in floats).  Returns 0, 1 (bad argument) or 2 (capacity too small). */
+int nb_debug_build_bvh(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes,
+                       float *nodes_out, uint64_t nodes_cap, float *tris_out, uint64_t tris_cap, uint32_t info[4]);
 /* Scene geometry summary after nb_build_accel. */
 int nb_scene_info(nb_ctx *, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_bytes, int *bvh_depth);
 

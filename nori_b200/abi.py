@@ -90,6 +90,7 @@ def lib():
         L.nb_film_to_rgb.argtypes = [vp, vp, vp]
         L.nb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         L.nb_debug_counters.argtypes = [vp, vp]
+        L.nb_debug_build_bvh.argtypes = [vp, vp, u32, i, C.c_int64, vp, u64, vp, u64, vp]
         L.nb_scene_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i)]
         _lib = L
     return _lib
@@ -102,6 +103,23 @@ def _p(a):
 def _check(rc):
     if rc != 0:
         raise NoriError(lib().nb_last_error().decode())
+
+
+def debug_build_bvh(V: np.ndarray, F: np.ndarray, max_leaf=3, bfs_nodes=2048):
+    """Runs the product's host SAH builder without a GPU (nb_debug_build_bvh).  V (nv,3) float32, F (nf,3) uint32.
+    Returns (nodes [n,16] float32, tris [m,12] float32, info dict)."""
+    L = lib()
+    v4 = np.zeros((V.shape[0], 4), dtype=np.float32); v4[:, :3] = V
+    f4 = np.zeros((F.shape[0], 4), dtype=np.uint32); f4[:, :3] = F
+    info = np.zeros(4, dtype=np.uint32)
+    _check_rc = L.nb_debug_build_bvh(_p(v4), _p(f4), F.shape[0], max_leaf, bfs_nodes, None, 0, None, 0, _p(info))
+    if _check_rc:
+        raise NoriError(f"nb_debug_build_bvh failed ({_check_rc})")
+    nodes = np.zeros((int(info[0]), 16), dtype=np.float32); tris = np.zeros((int(info[1]), 12), dtype=np.float32)
+    rc = L.nb_debug_build_bvh(_p(v4), _p(f4), F.shape[0], max_leaf, bfs_nodes, _p(nodes), nodes.size, _p(tris), tris.size, _p(info))
+    if rc:
+        raise NoriError(f"nb_debug_build_bvh failed ({rc})")
+    return nodes, tris, dict(nodes=int(info[0]), tris=int(info[1]), top_nodes=int(info[2]), depth=int(info[3]))
 
 
 class Context:

@@ -359,3 +359,17 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
 }
 
 }  // namespace nb
+
+// Host-only diagnostic entry (declared in include/nori_b200.h): runs the SAH builder on caller-provided arrays and
+// returns the device layout, so that the hierarchy can be checked without a GPU (tests/test_bvh_cpu.py).
+extern "C" int nb_debug_build_bvh(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes,
+                                  float *nodes_out, uint64_t nodes_cap, float *tris_out, uint64_t tris_cap, uint32_t info[4]) {
+    if ((nprims && (!verts4 || !faces4)) || !info || max_leaf < 1 || max_leaf > 8) return 1;
+    nb::BvhInput in; in.verts = verts4; in.faces = faces4; in.nprims = nprims;
+    nb::BvhOutput out;
+    nb::build_bvh(in, out, max_leaf, bfs_nodes < 0 ? nb::kSiblingPairs : (uint32_t) bfs_nodes, 0);
+    info[0] = out.nnodes; info[1] = (uint32_t) (out.tris.size() / 12); info[2] = out.top_nodes; info[3] = (uint32_t) out.depth;
+    if (nodes_out) { if (nodes_cap < out.nodes.size()) return 2; std::memcpy(nodes_out, out.nodes.data(), out.nodes.size() * sizeof(float)); }
+    if (tris_out) { if (tris_cap < out.tris.size()) return 2; if (!out.tris.empty()) std::memcpy(tris_out, out.tris.data(), out.tris.size() * sizeof(float)); }
+    return 0;
+}

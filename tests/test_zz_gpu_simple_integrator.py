@@ -82,17 +82,17 @@ def test_ttest_object_through_cli(tmp_path):
     for i in range(1, 6):
         path = host.write_xml(FX.polylum_scene(i, S.INT_PATH_MIS), str(tmp_path), f"poly{i}")
         parts.append(open(path).read().split("\n", 1)[1])           # drop the <?xml ...?> line
-    def test_file(name, refs):
+    def make_test_file(name, refs):
         p = tmp_path / name
         p.write_text('<test type="ttest">\n<string name="references" value="' + ", ".join("%.7g" % r for r in refs) + '"/>\n' + "".join(parts) + "</test>\n")
         return str(p)
     if not os.path.exists(host.CLI_PATH):
         from nori_b200 import build as nb_build
         nb_build.build_host(force=True)
-    good = subprocess.run([host.CLI_PATH, test_file("good.xml", FX.POLYLUM_REFS)], capture_output=True, text=True, timeout=600)
+    good = subprocess.run([host.CLI_PATH, make_test_file("good.xml", FX.POLYLUM_REFS)], capture_output=True, text=True, timeout=600)
     assert good.returncode == 0 and "Passed 5/5 tests." in good.stdout, good.stdout[-2000:] + good.stderr
     wrong = list(FX.POLYLUM_REFS); wrong[2] *= 1.2
-    bad = subprocess.run([host.CLI_PATH, test_file("bad.xml", wrong)], capture_output=True, text=True, timeout=600)
+    bad = subprocess.run([host.CLI_PATH, make_test_file("bad.xml", wrong)], capture_output=True, text=True, timeout=600)
     assert bad.returncode != 0 and "Passed 4/5 tests." in bad.stdout and "Some tests failed" in bad.stderr
 
 
