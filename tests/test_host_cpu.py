@@ -230,3 +230,37 @@ def test_write_xml_simple_round_trip(tmp_path):
     i = h.info()
     assert (i["integrator"], i["width"], i["height"], i["spp"]) == (S.INT_SIMPLE, 40, 30, 2)
     h.close()
+
+
+def test_parser_and_obj_loader_survive_mutated_input(tmp_path):
+    """Robustness: randomly damaged scene / OBJ text must end in a NoriException (or a valid scene), never in a crash or
+    a hang -- the reference gets this from pugixml and stream extraction; this mirror has its own readers."""
+    import random
+    rnd = random.Random(1234)
+    obj = "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvn 0 0 1\nvn 0 1 0\nvt 0 0\nvt 1 1\nf 1/1/1 2/2/1 3/1/2\nf 2/1/1 4/2/2 3/1/1\nf 1/1/1 2/2/2 3/1/1 4/2/2\n"
+    xml = ('<?xml version="1.0"?><scene><integrator type="path_mis"/><sampler type="independent"><integer name="sampleCount" value="4"/></sampler>'
+           '<camera type="perspective"><transform name="toWorld"><scale value="1,1,1"/><rotate angle="30" axis="0,1,0"/>'
+           '<lookat target="0,0,0" origin="0,0,5" up="0,1,0"/><translate value="0, 0, 1"/></transform><float name="fov" value="30"/>'
+           '<integer name="width" value="8"/><integer name="height" value="8"/><rfilter type="gaussian"/></camera>'
+           '<mesh type="obj"><string name="filename" value="m.obj"/><bsdf type="microfacet"><color name="kd" value="0.2,0.2,0.4"/>'
+           '<float name="alpha" value="0.3"/></bsdf><emitter type="area"><color name="radiance" value="1 1 1"/></emitter></mesh><!-- c --></scene>')
+    tokens = ['<', '>', '"', "'", '/', '=', '&', ' ', '\n', 'x', '-', '1e99', '<!--', '&amp;', '<a>', '</scene>', '\x00', '//', 'nan', '99999999999']
+
+    def mutate(text):
+        s = list(text)
+        for _ in range(rnd.randint(1, 5)):
+            i = rnd.randrange(len(s)); op = rnd.random()
+            if op < 0.35: del s[i:i + rnd.randint(1, 10)]
+            elif op < 0.7: s.insert(i, rnd.choice(tokens))
+            else: s[i] = rnd.choice('<>"\'/= &x0\n-.')
+        return "".join(s)
+
+    loaded = failed = 0
+    for k in range(150):
+        (tmp_path / "m.obj").write_text(mutate(obj) if k % 2 else obj)
+        (tmp_path / "s.xml").write_text(xml if k % 2 else mutate(xml))
+        try:
+            host.HostScene(tmp_path / "s.xml").close(); loaded += 1
+        except abi.NoriError:
+            failed += 1
+    assert loaded + failed == 150 and failed > 50
