@@ -129,6 +129,16 @@ int nb_set_point_light(nb_ctx *, const float position[3], const float energy[3])
  * the one given to nb_set_sampler.  Needs scene, camera and integrator; film, filter and tiling are not used. */
 int nb_li_samples(nb_ctx *, uint64_t n, float *lum_host, nb_stats *stats /* nullable */);
 
+/* Batched BSDF::sample() and BSDF::eval() + pdf() (ref: include/nori/bsdf.h:59-87) in local shading coordinates, for the
+ * callers of the BSDF plugins outside the render loop -- the reference's t-test in BSDF mode and its chi^2 test
+ * (ref: src/ttest.cpp:104-125, src/chi2test.cpp:113-153).  No scene is needed.  wi: 3 floats, shared by the whole batch
+ * (wi_per_query = 0; both tests fix wi) or 3 per query (wi_per_query = 1).
+ *   nb_bsdf_sample:   xi 2 floats per query; out8 = wo.xyz, weight.rgb (= eval * cos / pdf, 0 for a failed sample),
+ *                     pdf(wi, wo) (0 for discrete lobes), measure (1 solid angle, 2 discrete)
+ *   nb_bsdf_eval_pdf: wo 3 floats per query; out4 = eval.rgb, pdf  (solid-angle measure) */
+int nb_bsdf_sample(nb_ctx *, const nb_bsdf_desc *, const float *wi, int wi_per_query, const float *xi, uint64_t n, float *out8);
+int nb_bsdf_eval_pdf(nb_ctx *, const nb_bsdf_desc *, const float *wi, int wi_per_query, const float *wo, uint64_t n, float *out4);
+
 /* Tile sharding across GPUs: this context renders only 32x32 tiles with tile_id % nranks == rank
  * (tile_id = by * ceil(W/32) + bx).  Default (0, 1) = all tiles.  Replaces BlockGenerator::next
  * as the work scheduler (ref: src/block.cpp:119-152). */

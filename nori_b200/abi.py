@@ -84,6 +84,8 @@ def lib():
         L.nb_merge_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
         L.nb_merge_all_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
         L.nb_li_samples.argtypes = [vp, u64, vp, sp]
+        L.nb_bsdf_sample.argtypes = [vp, C.POINTER(BsdfDesc), vp, i, vp, u64, vp]
+        L.nb_bsdf_eval_pdf.argtypes = [vp, C.POINTER(BsdfDesc), vp, i, vp, u64, vp]
         L.nb_intersect.argtypes = [vp, vp, u64, vp, i, sp]
         L.nb_intersect_device.argtypes = [vp, vp, u64, vp, i, vp, sp]
         L.nb_intersect_full.argtypes = [vp, vp, u64, vp]
@@ -257,6 +259,20 @@ class Context:
         st = Stats()
         _check(lib().nb_li_samples(self.h, n, _p(lum), C.byref(st)))
         return lum, st
+
+    def bsdf_sample(self, bsdf: "BsdfDesc", wi: np.ndarray, xi: np.ndarray):
+        """nb_bsdf_sample: wi (3,) shared or (n,3); xi (n,2) -> (n,8) = wo, weight, pdf, measure."""
+        wi = np.ascontiguousarray(wi, dtype=np.float32); xi = np.ascontiguousarray(xi, dtype=np.float32)
+        out = np.zeros((xi.shape[0], 8), dtype=np.float32)
+        _check(lib().nb_bsdf_sample(self.h, C.byref(bsdf), _p(wi), int(wi.ndim == 2), _p(xi), xi.shape[0], _p(out)))
+        return out
+
+    def bsdf_eval_pdf(self, bsdf: "BsdfDesc", wi: np.ndarray, wo: np.ndarray):
+        """nb_bsdf_eval_pdf: wi (3,) shared or (n,3); wo (n,3) -> (n,4) = eval rgb, pdf."""
+        wi = np.ascontiguousarray(wi, dtype=np.float32); wo = np.ascontiguousarray(wo, dtype=np.float32)
+        out = np.zeros((wo.shape[0], 4), dtype=np.float32)
+        _check(lib().nb_bsdf_eval_pdf(self.h, C.byref(bsdf), _p(wi), int(wi.ndim == 2), _p(wo), wo.shape[0], _p(out)))
+        return out
 
     def intersect(self, rays: np.ndarray, shadow=False):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

@@ -5,6 +5,7 @@
 
 struct nb_ctx;
 struct nb_stats;
+struct nb_bsdf_desc;
 
 NORI_NAMESPACE_BEGIN
 
@@ -18,6 +19,9 @@ struct RenderOptions {
 /// Builds the GPU context for a scene: meshes + plugin descriptors (from the factory's creation records), BVH,
 /// camera, tabulated filter, sampler, integrator.  Throws NoriException on anything the device path cannot run.
 nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const RenderOptions &opt);
+
+/// POD descriptor of a BSDF plugin instance (from its creation record); throws for plugins without a device implementation.
+void describeBSDF(const BSDF *bsdf, nb_bsdf_desc *out);
 
 /// Replaces the body of render(): fills `result` (the full-image ImageBlock) through nb_render.
 void renderScene(Scene *scene, ImageBlock &result, const RenderOptions &opt, nb_stats *stats = nullptr);

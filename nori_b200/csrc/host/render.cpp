@@ -70,6 +70,8 @@ nb_integrator_desc describeIntegrator(const Integrator *integ) {
 
 }  // namespace
 
+void describeBSDF(const BSDF *bsdf, nb_bsdf_desc *out) { *out = describeBSDF(bsdf); }
+
 nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const RenderOptions &opt) {
     nb_ctx *ctx = nb_create(opt.device);
     if (!ctx) throwLast("nb_create");
@@ -197,7 +199,7 @@ int nori_host_mesh(void *scene_, int i, uint32_t *nv, uint32_t *nf, const float 
         *nv = m->getVertexCount(); *nf = m->getTriangleCount();
         *V = m->getVertexPositions().data(); *N = m->getVertexNormals().empty() ? nullptr : m->getVertexNormals().data();
         *UV = m->getVertexTexCoords().empty() ? nullptr : m->getVertexTexCoords().data(); *F = m->getIndices().data();
-        *bsdf = nori::describeBSDF(m->getBSDF());
+        nori::describeBSDF(m->getBSDF(), bsdf);
         nori::describeEmitter(m->getEmitter(), *emitter);
         return 0;
     } catch (const std::exception &e) { g_host_err = e.what(); return 1; }

@@ -670,6 +670,49 @@ int nb_li_samples(nb_ctx *c, uint64_t n, float *lum_host, nb_stats *st) {
     return rc;
 }
 
+// defined in nb_aux.cu (own translation unit: see the note there)
+cudaError_t nb_aux_launch_bsdf_query(const void *devmesh, size_t devmesh_bytes, unsigned long long n, const float *wi, int wi_stride,
+                                     const float *a, int mode, float *out, int grid, cudaStream_t s);
+
+namespace {
+int bsdf_query(nb_ctx *c, const nb_bsdf_desc *b, const float *wi, int wi_per_query, const float *a, int a_width, uint64_t n,
+               float *out, int out_width, int mode) {
+    if (!c || !b || (n && (!wi || !a || !out))) return fail("null argument");
+    if (b->type < NB_BSDF_DIFFUSE || b->type > NB_BSDF_MICROFACET) return fail("unsupported BSDF type %d (no CPU fallback)", b->type);
+    if (ensure_device(c)) return 1;
+    if (n == 0) return 0;
+    nb::DevMesh m;
+    memset(&m, 0, sizeof m);
+    m.bsdf_type = b->type; memcpy(m.albedo, b->albedo, sizeof m.albedo);
+    m.alpha = b->alpha; m.intIOR = b->intIOR; m.extIOR = b->extIOR; m.ks = b->ks;
+    const size_t wi_floats = wi_per_query ? 3 * n : 3;
+    float *dwi = nullptr, *da = nullptr, *dout = nullptr;
+    cudaError_t e = cudaMalloc(&dwi, sizeof(float) * wi_floats);
+    if (e == cudaSuccess) e = cudaMalloc(&da, sizeof(float) * a_width * n);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, sizeof(float) * out_width * n);
+    cudaStream_t s = c->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dwi, wi, sizeof(float) * wi_floats, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(da, a, sizeof(float) * a_width * n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        const int grid = (int) std::min<uint64_t>((n + 127) / 128, (uint64_t) c->sm_count * 16);
+        e = nb_aux_launch_bsdf_query(&m, sizeof m, n, dwi, wi_per_query ? 3 : 0, da, mode, dout, grid, s);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, sizeof(float) * out_width * n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dwi); cudaFree(da); cudaFree(dout);
+    if (e != cudaSuccess) return fail("BSDF query failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace
+
+int nb_bsdf_sample(nb_ctx *c, const nb_bsdf_desc *b, const float *wi, int wi_per_query, const float *xi, uint64_t n, float *out8) {
+    return bsdf_query(c, b, wi, wi_per_query, xi, 2, n, out8, 8, 0);
+}
+
+int nb_bsdf_eval_pdf(nb_ctx *c, const nb_bsdf_desc *b, const float *wi, int wi_per_query, const float *wo, uint64_t n, float *out4) {
+    return bsdf_query(c, b, wi, wi_per_query, wo, 3, n, out4, 4, 1);
+}
+
 int nb_intersect_device(nb_ctx *c, const nb_ray *rays_dev, uint64_t n, nb_hit *hits_dev, int shadow, void *stream, nb_stats *st) {
     if (!c) return fail("null context");
     if (ensure_device(c)) return 1;

@@ -345,6 +345,14 @@ void orc_bsdf_eval(const orc_bsdf *b, const float wi[3], const float wo[3], floa
     v3 f = bsdf_eval(b, ld3(wi), ld3(wo)); out[0] = f.x; out[1] = f.y; out[2] = f.z;
 }
 float orc_bsdf_pdf(const orc_bsdf *b, const float wi[3], const float wo[3]) { return bsdf_pdf(b, ld3(wi), ld3(wo)); }
+/* eval + pdf of n outgoing directions for one wi: out4 = eval.rgb, pdf (the checker of nb_bsdf_eval_pdf; also lets the
+ * chi^2 fixture integrate pdf() with as many nodes as a narrow lobe needs) */
+void orc_bsdf_eval_pdf_batch(const orc_bsdf *b, const float wi[3], const float *wo, uint64_t n, float *out4) {
+    for (uint64_t k = 0; k < n; ++k) {
+        v3 f = bsdf_eval(b, ld3(wi), ld3(wo + 3 * k));
+        out4[4 * k] = f.x; out4[4 * k + 1] = f.y; out4[4 * k + 2] = f.z; out4[4 * k + 3] = bsdf_pdf(b, ld3(wi), ld3(wo + 3 * k));
+    }
+}
 
 /* ------------------------------------------------------------------ reconstruction filters
  * ref: src/rfilter.cpp:16-108 (eval) tabulated as in src/block.cpp:19-27. kind: 0 gaussian 1 mitchell 2 tent 3 box */

@@ -121,6 +121,7 @@ void  orc_coordinate_system(const float a[3], float b[3], float c[3]);
 void  orc_bsdf_sample(const orc_bsdf *, const float wi[3], const float xi[2], float wo[3], float *eta, int *measure, float weight[3]);
 void  orc_bsdf_eval(const orc_bsdf *, const float wi[3], const float wo[3], float out[3]);
 float orc_bsdf_pdf(const orc_bsdf *, const float wi[3], const float wo[3]);
+void  orc_bsdf_eval_pdf_batch(const orc_bsdf *, const float wi[3], const float *wo, uint64_t n, float *out4);
 /* n samples from one continuing rng stream (ref: src/ttest.cpp:116-118, src/chi2test.cpp:113-115); wo_out nullable */
 int   orc_bsdf_sample_batch(const orc_bsdf *, const float wi[3], uint64_t n, orc_pcg32 *rng, float *wo_out, float *weight_out);
 void  orc_filter_table(int kind, float radius, float stddev, float B, float C, float table[33], float *radius_out);

@@ -93,6 +93,7 @@ def lib():
         L.orc_bsdf_eval.argtypes = [C.POINTER(Bsdf), vp, vp, vp]
         L.orc_bsdf_pdf.argtypes = [C.POINTER(Bsdf), vp, vp]; L.orc_bsdf_pdf.restype = C.c_float
         L.orc_bsdf_sample_batch.argtypes = [C.POINTER(Bsdf), vp, C.c_uint64, C.POINTER(Pcg32), vp, vp]
+        L.orc_bsdf_eval_pdf_batch.argtypes = [C.POINTER(Bsdf), vp, vp, C.c_uint64, vp]
         L.orc_filter_table.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, fp]
         L.orc_camera_matrices.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp]
         L.orc_sample_ray.argtypes = [vp, C.c_float, C.c_float, vp]

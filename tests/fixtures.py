@@ -69,3 +69,40 @@ def chi2_pvalue(obs: np.ndarray, exp: np.ndarray, min_exp: float = 5.0):
     if dof <= 0:
         return 1.0
     return float(stats.chi2.sf(chsq, dof))
+
+
+def integrate_cells(pdf_batch, ct_res: int, phi_res: int, rel_tol: float = 1e-5):
+    """Integral of a directional density over every (cos theta, phi) cell of the chi^2 contingency table
+    (ref: src/chi2test.cpp:126-153, where hypothesis::adaptiveSimpson2D does it).  Composite Simpson in (theta, phi)
+    -- theta, not cos theta: sin(theta) = sqrt(1 - c^2) has an unbounded derivative at c = 1 and stalls Simpson in the
+    top row -- with the intervals per axis doubled per cell until the value moves by less than rel_tol (a narrow
+    specular lobe at grazing incidence needs 128).  pdf_batch(wo[n,3] float32) -> pdf[n].  Same scheme as
+    nori_b200/csrc/host/stat_tests.cpp:integrateCells."""
+    res = ct_res * phi_res
+    dc, dp = 2.0 / ct_res, 2 * np.pi / phi_res
+    value = np.zeros(res); prev = np.full(res, -1.0)
+    todo = np.arange(res)
+    S = 16
+    while todo.size:
+        a = np.arange(S + 1)
+        w1 = np.where((a == 0) | (a == S), 1.0, np.where(a % 2 == 1, 4.0, 2.0))
+        i, j = todo // phi_res, todo % phi_res
+        t0 = np.arccos(np.minimum(1.0, -1.0 + (i + 1) * dc)); t1 = np.arccos(np.maximum(-1.0, -1.0 + i * dc))
+        th = t0[:, None] + (t1 - t0)[:, None] * a[None, :] / S                      # [cells, S+1]
+        ph = (j[:, None] + a[None, :] / S) * dp                                     # [cells, S+1]
+        sn = np.sin(th)
+        # the density jumps at the horizon, which is a cell boundary: a node ON it must be evaluated from its own cell's
+        # side (cos(pi/2) rounds to +6e-17, which would leak the upper-hemisphere value into the cell below)
+        c_lo, c_hi = (-1.0 + i * dc)[:, None], (-1.0 + (i + 1) * dc)[:, None]
+        cs = np.clip(np.cos(th), c_lo, c_hi)
+        cs = np.where(c_lo >= 0, np.maximum(cs, 1e-6), cs)
+        sd = np.sqrt(np.maximum(0.0, 1.0 - cs * cs))
+        wo = np.stack([sd[:, :, None] * np.cos(ph)[:, None, :], sd[:, :, None] * np.sin(ph)[:, None, :],
+                       np.broadcast_to(cs[:, :, None], (todo.size, S + 1, S + 1))], axis=-1).astype(np.float32)
+        pdf = pdf_batch(wo.reshape(-1, 3)).reshape(todo.size, S + 1, S + 1).astype(np.float64)
+        v = np.einsum("a,b,ca,cab->c", w1, w1, sn, pdf) * ((t1 - t0) / S / 3.0) * (dp / S / 3.0)
+        done = (prev[todo] >= 0) & (np.abs(v - prev[todo]) <= rel_tol * np.abs(v) + 1e-10)
+        value[todo] = v; prev[todo] = v
+        todo = todo[~done] if S < 1024 else todo[:0]
+        S *= 2
+    return value

@@ -12,7 +12,7 @@ from nori_b200 import scene as S
 
 def test_every_hot_path_plugin_is_registered():
     names = ["scene", "obj", "diffuse", "mirror", "dielectric", "microfacet", "area", "independent", "perspective",
-             "gaussian", "mitchell", "tent", "box", "normals", "ao", "whitted", "path_mats", "path_ems", "path_mis", "simple", "ttest"]
+             "gaussian", "mitchell", "tent", "box", "normals", "ao", "whitted", "path_mats", "path_ems", "path_mis", "simple", "ttest", "chi2test"]
     assert all(host.is_registered(n) for n in names)
     assert not host.is_registered("photonmapper")
 
@@ -144,11 +144,11 @@ REF_SCENES = "/root/reference/scenes"
 REF_SCENE_GAPS = {
     "pa2/ajax-normals.xml": "ajax.obj", "pa3/ajax-ao.xml": "ajax.obj", "pa5/ajax/ajax-rough.xml": "ajax.obj",
     "pa5/ajax/ajax-smooth.xml": "ajax.obj", "pa3/ajax-simple.xml": "ajax.obj",   # mesh not shipped with the reference
-    # `ttest` in scene mode parses, builds its scenes and then needs the device (nb_li_samples): no GPU in this container
+    # `ttest` / `chi2test` parse, build their children and then need the device (nb_li_samples, nb_bsdf_*): no GPU in this container
     "pa4/tests/test-mesh.xml": "no CUDA device|is not a scene", "pa4/tests/test-mesh-furnace.xml": "no CUDA device|is not a scene",
     "pa5/tests/test-direct.xml": "no CUDA device|is not a scene", "pa5/tests/test-furnace.xml": "no CUDA device|is not a scene",
-    "pa5/tests/ttest-microfacet.xml": "BSDF mode has no device implementation", "pa5/tests/chi2test-microfacet.xml": 'class "chi2test"',
-}                                                                  # BSDF-mode runners: restated in tests/fixtures.py instead
+    "pa5/tests/ttest-microfacet.xml": "no CUDA device|is not a scene", "pa5/tests/chi2test-microfacet.xml": "no CUDA device|is not a scene",
+}
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="reference checkout not present (GPU box)")
@@ -217,10 +217,46 @@ def test_ttest_object_statistics_and_errors(tmp_path, capfd):
     with pytest.raises(abi.NoriError, match="different number of scenes and reference values"):
         host.HostScene(bad)
     bsdf = tmp_path / "bsdf.xml"
-    bsdf.write_text('<test type="ttest"><string name="angles" value="0"/><string name="references" value="0.5"/><bsdf type="diffuse"/></test>')
-    with pytest.raises(abi.NoriError, match="BSDF mode has no device implementation"):
+    bsdf.write_text('<test type="ttest"><string name="angles" value="0, 10"/><string name="references" value="0.5"/><bsdf type="diffuse"/></test>')
+    with pytest.raises(abi.NoriError, match="different number of angles and reference values"):
         host.HostScene(bsdf)
+    both = tmp_path / "both.xml"
+    both.write_text('<test type="ttest"><string name="angles" value="0"/><string name="references" value="0.5"/><bsdf type="diffuse"/>' + scene + '</test>')
+    with pytest.raises(abi.NoriError, match="Cannot test BSDFs and scenes at the same time"):
+        host.HostScene(both)
+    chi = tmp_path / "chi.xml"
+    chi.write_text('<test type="chi2test"><integer name="resolution" value="4"/>' + scene + '</test>')
+    with pytest.raises(abi.NoriError, match=r"ChiSquareTest::addChild\(<scene>\) is not supported"):
+        host.HostScene(chi)
     capfd.readouterr()
+
+
+def test_chi2_object_statistics():
+    """chi^2 arithmetic of the `chi2test` object (ref: src/chi2test.cpp:171-173 via hypothesis::chi2_test): p-values against
+    scipy, pooling decisions against the restatement the oracle tests use (tests/fixtures.py:chi2_pvalue)."""
+    import ctypes as C
+    from scipy import stats
+    from tests import fixtures as FX
+    L = host.lib()
+    L.nori_host_chi2_pvalue.restype = C.c_double
+    L.nori_host_chi2_pvalue.argtypes = [C.c_double, C.c_int]
+    dp = C.POINTER(C.c_double)
+    L.nori_host_chi2_test.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, dp]
+    for x, dof in [(0.0, 5), (3.2, 1), (10.0, 10), (180.0, 199), (260.0, 199), (400.0, 150), (1.0, 120), (5000.0, 199)]:
+        assert L.nori_host_chi2_pvalue(x, dof) == pytest.approx(stats.chi2.sf(x, dof), rel=1e-9, abs=1e-300)
+    rng = np.random.default_rng(9)
+    for trial in range(40):
+        cells, n = 200, 1_000_000
+        p = rng.random(cells) ** 6                      # many low-expectation cells -> pooling
+        p[rng.integers(0, cells, 10)] = 0.0             # and some empty ones
+        p /= p.sum()
+        exp = p * n
+        obs = rng.multinomial(n, p if trial % 3 else np.roll(p, 1) * 0.999 + 0.001 / cells).astype(np.float64)
+        pv = C.c_double()
+        ok = L.nori_host_chi2_test(cells, obs.ctypes.data_as(dp), exp.ctypes.data_as(dp), n, 5.0, FX.SIGNIFICANCE, 15, C.byref(pv))
+        ref = FX.chi2_pvalue(obs, exp, 5.0)
+        assert pv.value == pytest.approx(ref, rel=1e-7, abs=1e-12)
+        assert bool(ok) == bool(ref > FX.sidak(FX.SIGNIFICANCE, 15))
 
 
 def test_write_xml_simple_round_trip(tmp_path):

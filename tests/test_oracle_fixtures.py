@@ -66,19 +66,23 @@ CHI2_BSDFS = [  # ref: scenes/pa5/tests/chi2test-microfacet.xml:5-24
 
 
 def test_chi2_microfacet(oracle):
-    """ref: src/chi2test.cpp:79-173 -- sample() histogram vs integrated pdf(), 10x20 bins, 5 wi per BSDF."""
+    """ref: scenes/pa5/tests/chi2test-microfacet.xml through src/chi2test.cpp:79-173 -- sample() histogram against the
+    integral of pdf() over 10 x 20 (cos theta, phi) cells, 5 incident directions per BSDF, ONE default-seeded pcg32
+    consumed in the reference's order.  All 15 cases must be accepted at the Sidak-corrected 1 % level, the
+    alpha = 0.1 pure-specular lobe at grazing incidence included (that one needs the converged quadrature of
+    fixtures.integrate_cells; a fixed 8 x 8 midpoint rule rejects it)."""
     L = oracle.lib()
     rng = oracle.Pcg32(); L.orc_pcg32_init(C.byref(rng))
     ct_res, phi_res = 10, 20
     n = ct_res * phi_res * 5000
     thr = FX.sidak(0.01, 5 * len(CHI2_BSDFS))
-    sub = 8   # midpoint sub-cells per bin axis for the pdf integral (adaptiveSimpson2D in the reference)
+    pvals = []
     for p in CHI2_BSDFS:
         bs = oracle.bsdf_struct(S.microfacet(p["kd"], p["alpha"], p["intIOR"], p["extIOR"]))
         for _ in range(5):
-            cos_t = L.orc_pcg32_next_float(C.byref(rng))
-            sin_t = np.sqrt(max(0.0, 1 - cos_t * cos_t))
-            ph = 2 * np.pi * L.orc_pcg32_next_float(C.byref(rng))
+            cos_t = np.float32(L.orc_pcg32_next_float(C.byref(rng)))
+            sin_t = np.float32(np.sqrt(max(np.float32(0.0), np.float32(1) - cos_t * cos_t)))
+            ph = np.float32(2 * np.pi) * np.float32(L.orc_pcg32_next_float(C.byref(rng)))
             wi = np.array([np.cos(ph) * sin_t, np.sin(ph) * sin_t, cos_t], dtype=np.float32)
             wo = np.zeros((n, 3), np.float32); w = np.zeros((n, 3), np.float32)
             L.orc_bsdf_sample_batch(C.byref(bs), oracle._p(wi), n, C.byref(rng), oracle._p(wo), oracle._p(w))
@@ -88,24 +92,17 @@ def test_chi2_microfacet(oracle):
             sp[sp < 0] += 1
             pb = np.clip(np.floor(sp * phi_res).astype(int), 0, phi_res - 1)
             obs = np.bincount(ctb * phi_res + pb, minlength=ct_res * phi_res).astype(np.float64)
-            exp = np.zeros(ct_res * phi_res)
-            wo1 = np.zeros(3, np.float32)
-            for i in range(ct_res):
-                for j in range(phi_res):
-                    acc = 0.0
-                    for a in range(sub):
-                        ct = -1.0 + (i + (a + 0.5) / sub) * 2.0 / ct_res
-                        if ct <= 0:
-                            continue
-                        st = np.sqrt(1 - ct * ct)
-                        for b in range(sub):
-                            phi = (j + (b + 0.5) / sub) * 2 * np.pi / phi_res
-                            wo1[:] = (st * np.cos(phi), st * np.sin(phi), ct)
-                            acc += L.orc_bsdf_pdf(C.byref(bs), oracle._p(wi), oracle._p(wo1))
-                    exp[i * phi_res + j] = acc * (2.0 / ct_res / sub) * (2 * np.pi / phi_res / sub) * n
-            # the midpoint rule is coarse near the specular peak for alpha=0.1: compare at a resolution it resolves
+
+            def pdf_batch(dirs):
+                out = np.zeros((dirs.shape[0], 4), np.float32)
+                dirs = np.ascontiguousarray(dirs)
+                L.orc_bsdf_eval_pdf_batch(C.byref(bs), oracle._p(wi), oracle._p(dirs), dirs.shape[0], oracle._p(out))
+                return out[:, 3]
+            exp = FX.integrate_cells(pdf_batch, ct_res, phi_res) * n
             pval = FX.chi2_pvalue(obs, exp)
-            assert pval > thr or p["alpha"] < 0.2, (p, wi, pval)
+            pvals.append(pval)
+            assert pval > thr, (p, wi, pval)
+    assert len(pvals) == 15
 
 
 @pytest.mark.parametrize("integrator", ["whitted", "path_ems", "path_mats", "path_mis"])
