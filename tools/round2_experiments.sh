@@ -6,7 +6,8 @@
 #   _compact : NB_COMPACT_PATH=1  -- tile rectangle re-derived at splat time (static spill bytes 650 -> 606 path, 222 -> 182 ao)
 #   _tail    : NB_TAIL_CUT=1      -- resumable walks; run time option "tail" (tools/tail_sweep.py sweeps it)
 #   _both    : both
-#   _p10/_p12: register cap of the path tracers re-swept now that waves are phased (11 CTAs/SM is the default)
+#   _p10/_p9 : register cap of the path tracers re-swept now that waves are phased (default 11 CTAs/SM = 40 registers,
+#              as is 12; 10 -> 48, 9 -> 56, 8 -> 64 which measured slower)
 if [ "$1" = "--build" ]; then
 python - <<'PY'
 from nori_b200 import build
@@ -15,7 +16,7 @@ build.build_cuda(force=True, variant="_compact", extra_flags=("-DNB_COMPACT_PATH
 build.build_cuda(force=True, variant="_tail", extra_flags=("-DNB_TAIL_CUT=1",))
 build.build_cuda(force=True, variant="_both", extra_flags=("-DNB_TAIL_CUT=1", "-DNB_COMPACT_PATH=1"))
 build.build_cuda(force=True, variant="_p10", extra_flags=("-DNB_MIN_BLOCKS_PATH=10",))
-build.build_cuda(force=True, variant="_p12", extra_flags=("-DNB_MIN_BLOCKS_PATH=12",))
+build.build_cuda(force=True, variant="_p9", extra_flags=("-DNB_MIN_BLOCKS_PATH=9",))
 PY
 exit $?
 fi
@@ -23,7 +24,7 @@ set -x
 # first of all: the entry points that have never run on hardware (simple integrator, nb_li_samples, ttest object)
 timeout 600 python -m pytest tests/test_zz_gpu_simple_integrator.py -q -rxX 2>&1 | tail -15
 bash tools/ab_variants.sh "default _compact default _compact" "ajax-ao cbox-mis"
-bash tools/ab_variants.sh "default _p10 _p12" "cbox-mis ajax-rough"
+bash tools/ab_variants.sh "default _p10 _p9" "cbox-mis ajax-rough"
 # a walk that never ends must not take the box with it: the earlier tail-cut build livelocked
 for lib in _tail _both; do
   NORI_B200_LIB=nori_b200/lib/libnori_b200$lib.so TAILS="0 2 4 8 12" timeout 90 python tools/tail_sweep.py ajax-ao cbox-mis
