@@ -46,6 +46,9 @@ namespace nb {
 #ifndef NB_COMPACT_PATH
 #define NB_COMPACT_PATH 0    // experiment: keep only tile_slot per lane, re-derive the tile rectangle at splat time
 #endif
+#ifndef NB_DEFER_SHADOW
+#define NB_DEFER_SHADOW 0    // 1 only in nb_wavefront.cu: occlusion rays (ao, next-event estimation, simple) go to a queue
+#endif
 #ifndef NB_SPLAT_HOIST
 #define NB_SPLAT_HOIST 1
 #endif
@@ -91,6 +94,10 @@ struct RenderParams {
     int32_t block_stream_skip;      // per-block seeding served by skip-ahead (fixed draws per sample)
     int32_t tail_lanes;             // a wave's walk is suspended once <= tail_lanes lanes are still walking (0 = never)
     float light_pos[3], light_energy[3];   // point light of the `simple` integrator (appended: older fields keep their offsets)
+    // deferred-occlusion engine (nb_wavefront.cu; unused by the kernels of nb_api.cu)
+    float4 *occ_queue;              // 4 x float4 per queued occlusion ray (OccRay)
+    uint32_t occ_capacity;          // rays the queue holds
+    int32_t slot_base;              // first owned-tile slot of this slice
 };
 
 // ------------------------------------------------------------------ traversal state (per lane)
@@ -235,7 +242,7 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
         if (leaf_test<COUNT>(sc, node, r, t, any_hit, n_tris)) break;
         node = sp ? stack[--sp] : kDone;
 #endif
-#if NB_TAIL_CUT
+#if NB_TAIL_CUT || NB_DEFER_SHADOW
         // ---- tail cut (experimental): when only a few lanes of the warp are still walking, they
         // keep their (node, stack) and the warp goes on to shade / refill the finished lanes; the walk resumes in the next
         // wave.  Checked at the END of an iteration so that every call makes progress (a check on entry livelocks as soon
@@ -378,6 +385,51 @@ __device__ __forceinline__ void splat(const RenderParams &P, int tile_slot, int 
     }
 }
 
+#if NB_DEFER_SHADOW
+// The filter is linear, so a sample's film contribution may be splatted in pieces: the path's own radiance with the
+// filter weight (splat above), and each unoccluded next-event / ambient-occlusion term later with weight 0.
+__device__ __forceinline__ void splat_contrib(const RenderParams &P, int tile_slot, float sx, float sy, V3 value) {
+    if (value.x < 0 || !isfinite(value.x) || value.y < 0 || !isfinite(value.y) || value.z < 0 || !isfinite(value.z)) return;
+    const int tile_id = P.tile_rank + tile_slot * P.tile_nranks;
+    const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+    const int tsx = min(32, P.W - tox), tsy = min(32, P.H - toy);
+    const int bd = P.border;
+    const float posx = sx - 0.5f - (float) (tox - bd), posy = sy - 0.5f - (float) (toy - bd);
+    int x0 = (int) ceilf(posx - P.fradius), y0 = (int) ceilf(posy - P.fradius);
+    int x1 = (int) floorf(posx + P.fradius), y1 = (int) floorf(posy + P.fradius);
+    x0 = max(x0, 0); y0 = max(y0, 0);
+    x1 = min(x1, tsx + 2 * bd - 1); y1 = min(y1, tsy + 2 * bd - 1);
+    float4 *blk = P.blocks + (size_t) tile_slot * P.block_edge * P.block_edge;
+    for (int y = y0; y <= y1; ++y) {
+        const float wy = P.ftable[(int) (fabsf((float) y - posy) * P.lookup)];
+        for (int x = x0; x <= x1; ++x) {
+            const float wx = P.ftable[(int) (fabsf((float) x - posx) * P.lookup)];
+            atomicAdd(&blk[y * P.block_edge + x], make_float4(value.x * wx * wy, value.y * wx * wy, value.z * wx * wy, 0.0f));
+        }
+    }
+}
+
+// Queue entry of one occlusion ray: [o.xyz, mint] [d.xyz, maxt] [contribution rgb, sx] [sy, tile slot, -, -]
+// Appends with one atomic per converged group of lanes; returns false when the queue is full (the caller then traces
+// the ray itself, exactly as the fused kernel does).
+__device__ __forceinline__ bool occ_push(const RenderParams &P, const Ray &r, V3 contrib, float sx, float sy, int tile_slot) {
+    const unsigned mask = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if ((int) lane == leader) base = atomicAdd(&P.counters[7], (unsigned long long) __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    const unsigned long long idx = base + (unsigned long long) __popc(mask & ((1u << lane) - 1u));
+    if (idx >= (unsigned long long) P.occ_capacity) return false;
+    float4 *q = P.occ_queue + idx * 4ull;
+    q[0] = make_float4(r.ox, r.oy, r.oz, r.mint);
+    q[1] = make_float4(r.dx, r.dy, r.dz, r.maxt);
+    q[2] = make_float4(contrib.x, contrib.y, contrib.z, sx);
+    q[3] = make_float4(sy, __int_as_float(tile_slot), 0.f, 0.f);
+    return true;
+}
+#endif
+
 // ------------------------------------------------------------------ emitter sampling [authored]; DiscretePDF::sample ref: include/nori/dpdf.h:93-99
 __device__ __forceinline__ uint32_t cdf_sample(const float *cdf, uint32_t n, float x) {
     uint32_t lo = 0, hi = n + 1;
@@ -425,6 +477,9 @@ struct Path {
     unsigned char tsx, tsy;  // tile size
     unsigned char stage;
     bool prev_specular, has_next;
+#if NB_DEFER_SHADOW
+    unsigned deferred;       // occlusion rays this lane handed to the queue (they count as traced rays)
+#endif
 };
 
 // One shading step after a ray finished.  Returns true when the path is complete (L final).
@@ -457,6 +512,9 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
         const V3 w = to_world(its.sh, square_to_cosine_hemisphere(x, y));
         ray.ox = its.p.x; ray.oy = its.p.y; ray.oz = its.p.z; ray.dx = w.x; ray.dy = w.y; ray.dz = w.z;
         ray.mint = NB_EPSILON; ray.maxt = NB_INF;
+#if NB_DEFER_SHADOW
+        if (occ_push(P, ray, mk(1, 1, 1), ps.sx, ps.sy, ps.tile_slot)) { ps.deferred++; return true; }   // L stays 0; visibility arrives through the queue
+#endif
         ps.stage = ST_SHADOW_AO;
         return false;
     }
@@ -472,6 +530,9 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
         ps.has_next = false;
         ray.ox = its.p.x; ray.oy = its.p.y; ray.oz = its.p.z; ray.dx = wo_w.x; ray.dy = wo_w.y; ray.dz = wo_w.z;
         ray.mint = NB_EPSILON; ray.maxt = dist - NB_EPSILON;
+#if NB_DEFER_SHADOW
+        if (occ_push(P, ray, ps.contrib, ps.sx, ps.sy, ps.tile_slot)) { ps.deferred++; return true; }
+#endif
         ps.stage = ST_SHADOW;                           // resolved by the ST_SHADOW branch above: L += contrib if unoccluded
         return false;
     }
@@ -560,6 +621,10 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
             ps.has_next = ps.depth < P.max_depth;
         }
     }
+#if NB_DEFER_SHADOW
+    // the shadow ray goes to the queue with its contribution; the path carries on with its extension ray at once
+    if (want_shadow && occ_push(P, sray, ps.contrib, ps.sx, ps.sy, ps.tile_slot)) { ps.deferred++; want_shadow = false; }
+#endif
     if (want_shadow) { ray = sray; ps.stage = ST_SHADOW; return false; }
     if (!ps.has_next) return true;
     ray.dx = ps.next_d.x; ray.dy = ps.next_d.y; ray.dz = ps.next_d.z; ray.mint = NB_EPSILON; ray.maxt = NB_INF;
@@ -629,6 +694,9 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
 #endif
     Path ps; Ray ray; Trav tr;
     ps.stage = ST_IDLE; tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu;
+#if NB_DEFER_SHADOW
+    ps.deferred = 0;
+#endif
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
     unsigned wave_nodes = 0; unsigned long long wave_max_sum = 0, n_waves = 0;
 
@@ -670,6 +738,9 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
                 const uint32_t rest = (uint32_t) (u / 32ULL);
                 const uint32_t chunk_id = rest % P.nchunks;
                 u_tile_slot = (int) (rest / P.nchunks);
+#if NB_DEFER_SHADOW
+                u_tile_slot += P.slot_base;               // this launch renders one slice of the owned tiles
+#endif
                 const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;
                 const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
                 u_tox = bx * 32; u_toy = by * 32;
@@ -742,6 +813,9 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     }
 
     // counters: warp-reduce then one atomic per warp
+#if NB_DEFER_SHADOW
+    n_rays += ps.deferred;
+#endif
     unsigned long long v1 = n_rays, v2 = n_nodes, v3 = n_tris, v4 = n_hits;
     for (int o = 16; o > 0; o >>= 1) {
         v1 += __shfl_down_sync(0xffffffffu, v1, o); v2 += __shfl_down_sync(0xffffffffu, v2, o);
@@ -813,6 +887,57 @@ __global__ void __launch_bounds__(128) li_samples_kernel(const __grid_constant__
     atomicAdd(&P.counters[1], (unsigned long long) n_rays);
     atomicAdd(&P.counters[4], (unsigned long long) n_hits);
 }
+
+#if NB_DEFER_SHADOW
+// ------------------------------------------------------------------ occlusion kernel of the deferred engine
+// Traces the queued occlusion rays (any hit) and splats the contribution of the unoccluded ones.  Persistent warps with
+// dynamic fetch: a lane keeps its walk (node, stack) across refills; the warp leaves the walk as soon as at most
+// tail_lanes lanes are still walking, lets the finished lanes splat and take new rays from the queue (one atomic per
+// refill), and resumes.  Occlusion rays are incoherent and of very uneven length, which is what makes them expensive in
+// the lock-step kernel; here the lanes stay busy.
+__global__ void __launch_bounds__(128, NB_MIN_BLOCKS) occlusion_kernel(const __grid_constant__ RenderParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int stack[kStack + 1];
+    Ray ray; Trav tr;
+    tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu; tr.hu = 0.f; tr.hv = 0.f;
+    V3 contrib = mk(0, 0, 0); float sx = 0.f, sy = 0.f; int tile_slot = 0;
+    bool active = false, exhausted = false;
+    unsigned long long n_in = P.counters[7];
+    if (n_in > (unsigned long long) P.occ_capacity) n_in = P.occ_capacity;
+    for (;;) {
+        // ---- refill (all 32 lanes are converged here)
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, !active);
+        if (idle_mask != 0u && !exhausted) {
+            const unsigned n_idle = __popc(idle_mask);
+            unsigned long long start = 0;
+            if (lane == 0) start = atomicAdd(&P.counters[0], (unsigned long long) n_idle);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            const unsigned long long idx = start + (unsigned long long) __popc(idle_mask & lt_mask);
+            if (!active && idx < n_in) {
+                const float4 *q = P.occ_queue + idx * 4ull;
+                const float4 a = q[0], b = q[1], c = q[2], d = q[3];
+                ray.ox = a.x; ray.oy = a.y; ray.oz = a.z; ray.mint = a.w;
+                ray.dx = b.x; ray.dy = b.y; ray.dz = b.z; ray.maxt = b.w;
+                contrib = mk(c.x, c.y, c.z); sx = c.w; sy = d.x; tile_slot = __float_as_int(d.y);
+                tr.node = kDone;                           // fresh ray for walk_wave
+                active = true;
+            }
+            if (start + (unsigned long long) n_idle >= n_in) exhausted = true;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        // ---- walk until at most tail_lanes lanes are left (to completion once the queue is drained)
+        if (active) {
+            unsigned nn = 0, nt = 0;
+            walk_wave<false, false>(P.sc.nodes, P.sc.tris, nullptr, 0, ray, tr, stack, true, exhausted ? 0 : P.tail_lanes, nn, nt);
+            if (tr.node == kDone) {
+                if (tr.hprim == 0xffffffffu) splat_contrib(P, tile_slot, sx, sy, contrib);
+                active = false;
+            }
+        }
+    }
+}
+#endif
 
 // ------------------------------------------------------------------ K6: merge finished blocks into the full film (ref: src/block.cpp:93-102)
 __global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank, int nranks, int ntx, int W, int H,

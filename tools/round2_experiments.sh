@@ -33,3 +33,10 @@ done
 for lib in _compact _tail; do
   NORI_B200_LIB=nori_b200/lib/libnori_b200$lib.so timeout 120 python -m pytest tests/test_gpu_parity.py -q -x -k "film_parity" 2>&1 | tail -2
 done
+
+# deferred-occlusion engine (nb_wavefront.cu): A/B against the fused kernel, refill threshold sweep
+for w in ajax-ao cbox-mis ajax-rough; do
+  for o in "engine=0" "engine=1" "engine=1 --opt occ_tail=12" "engine=1 --opt occ_tail=24" "engine=1 --opt occ_tail=28"; do
+    python bench.py --workload $w --steps 8 --warmup 3 --no-cpu-baseline --opt $o 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ENG','$w','[$o]',round(d['ms_per_step'],3),round(d['value'],1))"
+  done
+done
