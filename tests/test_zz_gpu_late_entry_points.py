@@ -165,32 +165,3 @@ def test_reference_bsdf_fixtures_through_cli(tmp_path):
         for a, i, e, kd in [(0.1, 1.33, 1.01, (0.0, 0.0, 0.0)), (0.3, 1.5, 1.01, (0.2, 0.1, 0.6)), (0.6, 1.8, 1.3, (0.4, 0.2, 0.3))]) + '</test>')
     r = subprocess.run([host.CLI_PATH, str(c)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "Passed 15/15 tests." in r.stdout, r.stdout[-1500:] + r.stderr
-
-
-@pytest.mark.parametrize("case", ["ao", "whitted", "path_mats", "path_ems", "path_mis", "simple", "microfacet"])
-def test_deferred_occlusion_engine_parity(oracle, case):
-    """nb_set_option("engine", 1): occlusion rays queued and traced by occlusion_kernel (nb_wavefront.cu).  Same rays, same
-    film (the contributions reach it in a different order), also when the queue is far too small (1 MB = 16 k rays: many
-    slices, and overflowing rays are traced by the render kernel itself)."""
-    if case == "ao":
-        cam = S.Camera(S.lookat(**S._AJAX_CAM).astype(np.float32), 30.0, 160, 120)
-        sc = S.Scene([S.ajax_standin(2)], cam, S.INT_AO, 8, name="deferred-ao")
-    elif case == "simple":
-        sc = simple_scene(160, 120, 8)
-    elif case == "microfacet":
-        sc = S.config_cbox(64, 64, 16, S.INT_PATH_MIS)
-        sc.meshes[3] = S.with_(sc.meshes[3], S.microfacet((0.2, 0.2, 0.4), 0.28, 1.7))
-        sc.meshes[4] = S.with_(sc.meshes[4], S.dielectric())
-    else:
-        sc = S.config_cbox(64, 64, 16, S.INTEGRATORS[case])
-    ofilm, ost = oracle.OracleScene(sc).render(accel=1)
-    with abi.Context(0) as ctx:
-        ctx.load(sc)
-        for occ_mb, occ_tail in ((1024, 20), (1, 8), (1, 0)):
-            ctx.set_option("engine", 1); ctx.set_option("occ_mb", occ_mb); ctx.set_option("occ_tail", occ_tail)
-            film, st = ctx.render()
-            assert st.samples == ost.samples and st.rays == ost.rays, (case, occ_mb, st.rays, ost.rays)
-            assert S.rel_l2(film, ofilm) <= TOL, (case, occ_mb, occ_tail)
-        ctx.set_option("engine", 0)
-        film0, st0 = ctx.render()
-        assert st0.rays == ost.rays and S.rel_l2(film0, ofilm) <= TOL

@@ -23,6 +23,7 @@ fi
 set -x
 # first of all: the entry points that have never run on hardware (simple integrator, nb_li_samples, ttest object)
 timeout 600 python -m pytest tests/test_zz_gpu_late_entry_points.py -q -rxX 2>&1 | tail -15
+NB_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_zzz_gpu_deferred_engine.py -q -x 2>&1 | tail -15
 bash tools/ab_variants.sh "default _compact default _compact" "ajax-ao cbox-mis"
 bash tools/ab_variants.sh "default _p10 _p9" "cbox-mis ajax-rough"
 # a walk that never ends must not take the box with it: the earlier tail-cut build livelocked
