@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NB_ABI_VERSION 1
+#define NB_ABI_VERSION 2
 #define NB_BLOCK_SIZE 32          /* ref: include/nori/block.h:17  NORI_BLOCK_SIZE */
 #define NB_FILTER_RESOLUTION 32   /* ref: include/nori/rfilter.h:12 */
 #define NB_MISS 0xffffffffu
@@ -85,6 +85,26 @@ nb_ctx *nb_create(int device);
 void    nb_destroy(nb_ctx *);
 const char *nb_last_error(void);
 int     nb_abi_version(void);
+
+/* ---- N GPUs behind the same calls (replaces the TBB tile loop + merge for N devices, ref: src/main.cpp:85-113,
+ * src/block.cpp:93-102).  nb_create_multi returns ONE context (on devices[0]) that owns a context per further device
+ * and the NCCL communicators between them (ncclCommInitAll; libnccl.so.2 is loaded on first use).  Every scene / camera /
+ * sampler / integrator / option call on it applies to all devices; nb_build_accel builds the hierarchy once and replicates
+ * the scene arrays over NVLink (ncclBroadcast); nb_render / nb_render_device shard the 32x32 tiles tile_id % ndev, gather
+ * the finished ImageBlocks on devices[0] with ONE grouped ncclSend/ncclRecv, merge them with ONE launch and return the
+ * full film.  ndev == 1 is exactly nb_create(devices[0]).  nb_device_count: devices behind a context (1 for nb_create). */
+nb_ctx *nb_create_multi(const int *devices, int ndev);
+int     nb_device_count(nb_ctx *);
+/* One process per GPU (torchrun, MPI): rank 0 draws a communicator id, the caller ships the 128 bytes to every rank by any
+ * means, each rank attaches its context.  From then on the context is rank `rank` of an `nranks`-GPU group: nb_build_accel
+ * builds on rank 0 only and replicates over NVLink (the other ranks need no meshes), nb_upload_scene crosses PCIe once,
+ * and nb_render / nb_render_gather render this rank's tile shard, gather on rank 0 and merge there (film is written on
+ * rank 0 only and may be NULL elsewhere).  All ranks must make the same sequence of these calls (they are collective). */
+#define NB_COMM_ID_BYTES 128
+int nb_comm_get_unique_id(uint8_t id[NB_COMM_ID_BYTES]);
+int nb_comm_init_rank(nb_ctx *, const uint8_t id[NB_COMM_ID_BYTES], int rank, int nranks);
+/* Device-film variant of the group render; stats == NULL only enqueues (no host synchronisation). */
+int nb_render_gather(nb_ctx *, float *film_dev, void *stream, nb_stats *stats);
 
 /* Replaces Accel::addMesh (ref: src/accel.cpp:12-17; called from Scene::addChild, ref: src/scene.cpp:48-53).
  * V: 3*nv floats packed xyz == m_V 3xN column-major (ref: include/nori/mesh.h:160); N (3*nv) and UV (2*nv)
@@ -153,7 +173,10 @@ int nb_render(nb_ctx *, float *film_host, nb_stats *stats);
 /* Same, but the film stays on the device (film_dev: device pointer on the context's device) and all work is
  * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the context's own stream).  Used by the
  * multi-GPU driver, which exchanges films with NCCL. */
-int nb_render_device(nb_ctx *, float *film_dev, void *stream, nb_stats *stats);
+int nb_render_device(nb_ctx *, float *film_dev, void *stream, nb_stats *stats);   /* stats == NULL: enqueue only, no host sync */
+/* Device time of the render kernel(s) of this context's last (finished) render call: CUDA events recorded around them on
+ * the launch stream.  For callers that enqueue frames without statistics and read the kernel time afterwards. */
+int nb_last_kernel_ms(nb_ctx *, double *ms);
 
 /* Finished ImageBlocks of this context's tiles, packed: blocks_dev receives ntiles_mine x (32+2b) x (32+2b) x 4 fp32
  * (tile order = ascending tile_id of the tiles owned by (rank, nranks)); the frame-end exchange gathers these. */

@@ -63,6 +63,11 @@ def lib():
         vp, i, u32, u64, f = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_float
         sp = C.POINTER(Stats)
         L.nb_create.argtypes = [i]; L.nb_create.restype = vp
+        L.nb_create_multi.argtypes = [C.POINTER(i), i]; L.nb_create_multi.restype = vp
+        L.nb_device_count.argtypes = [vp]
+        L.nb_comm_get_unique_id.argtypes = [vp]
+        L.nb_comm_init_rank.argtypes = [vp, vp, i, i]
+        L.nb_render_gather.argtypes = [vp, vp, vp, sp]
         L.nb_destroy.argtypes = [vp]; L.nb_destroy.restype = None
         L.nb_last_error.restype = C.c_char_p
         L.nb_abi_version.restype = i
@@ -79,6 +84,7 @@ def lib():
         L.nb_set_tiles.argtypes = [vp, i, i]
         L.nb_render.argtypes = [vp, vp, sp]
         L.nb_render_device.argtypes = [vp, vp, vp, sp]
+        L.nb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
         L.nb_render_blocks_device.argtypes = [vp, vp, vp, sp]
         L.nb_tile_count.argtypes = [vp, i, i, C.POINTER(i), C.POINTER(i)]
         L.nb_merge_blocks_device.argtypes = [vp, vp, i, i, vp, vp]
@@ -127,12 +133,44 @@ def debug_build_bvh(V: np.ndarray, F: np.ndarray, max_leaf=3, bfs_nodes=2048):
 class Context:
     """One GPU's render context (nb_ctx).  Mirrors the role of Scene's Accel + render() in the reference."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device=-1):
+        """device: one CUDA device index (nb_create), or a list of them -- ONE context driving all of them, tiles sharded
+        tile_id % N and gathered over NCCL behind nb_render (nb_create_multi)."""
         L = lib()
-        self.h = L.nb_create(device)
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*[int(d) for d in device])
+            self.h = L.nb_create_multi(arr, len(device))
+        else:
+            self.h = L.nb_create(int(device))
         if not self.h:
             raise NoriError(L.nb_last_error().decode())
         self.scene = None
+
+    @property
+    def device_count(self) -> int:
+        return int(lib().nb_device_count(self.h))
+
+    # ---- one process per GPU (torchrun): attach this context to an NCCL group
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(lib().nb_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init_rank(self, uid: bytes, rank: int, nranks: int):
+        assert len(uid) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        _check(lib().nb_comm_init_rank(self.h, buf, rank, nranks))
+
+    def render_gather(self, film_ptr: int, stream: int = 0, want_stats: bool = True):
+        """nb_render_gather: this rank's tile shard -> ONE NCCL gather of finished blocks on rank 0 -> ONE merge launch there.
+        film_ptr: device film on rank 0 (0 elsewhere).  want_stats=False only enqueues."""
+        if not want_stats:
+            _check(lib().nb_render_gather(self.h, C.c_void_p(film_ptr) if film_ptr else None, C.c_void_p(stream), None))
+            return None
+        st = Stats()
+        _check(lib().nb_render_gather(self.h, C.c_void_p(film_ptr) if film_ptr else None, C.c_void_p(stream), C.byref(st)))
+        return st
 
     def close(self):
         if getattr(self, "h", None):
@@ -233,10 +271,18 @@ class Context:
         _check(lib().nb_render(self.h, C.c_void_p(host_ptr), C.byref(st)))
         return st
 
-    def render_device(self, film_ptr: int, stream: int = 0):
+    def render_device(self, film_ptr: int, stream: int = 0, want_stats: bool = True):
+        if not want_stats:
+            _check(lib().nb_render_device(self.h, C.c_void_p(film_ptr), C.c_void_p(stream), None))
+            return None
         st = Stats()
         _check(lib().nb_render_device(self.h, C.c_void_p(film_ptr), C.c_void_p(stream), C.byref(st)))
         return st
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_double()
+        _check(lib().nb_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def render_blocks_device(self, blocks_ptr: int, stream: int = 0, want_stats: bool = True):
         """want_stats=False only enqueues the work on `stream` (no counter read-back, no host synchronisation)."""

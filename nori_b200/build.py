@@ -42,13 +42,27 @@ def _run(cmd, log_name):
 
 
 def build_cuda(force=False, variant="", extra_flags=()):
+    """nvcc, one object per translation unit (compiled concurrently), linked into libnori_b200<variant>.so."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB, exist_ok=True)
     target = os.path.join(LIB, f"libnori_b200{variant}.so")
     srcs = [os.path.join(CSRC, f) for f in ("nb_api.cu", "nb_aux.cu", "nb_wavefront.cu", "nb_bvh.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("nb_bvh.h", "nb_kernels.cuh", "nb_device.cuh", "nb_lbvh.cuh")] + \
-        [os.path.join(os.path.dirname(HERE), "include", "nori_b200.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("nb_bvh.h", "nb_kernels.cuh", "nb_device.cuh", "nb_lbvh.cuh", "nb_ctx.h", "nb_multi.inl", "nb_wide.h")
+                   if os.path.exists(os.path.join(CSRC, f))] + [os.path.join(os.path.dirname(HERE), "include", "nori_b200.h")]
     if force or _stale(target, deps):
-        _run([NVCC] + NVCC_FLAGS + list(extra_flags) + ["-shared", "-o", target] + srcs, f"build_cuda{variant}.log")
+        objdir = os.path.join(LIB, f"obj{variant}")
+        os.makedirs(objdir, exist_ok=True)
+        objs = [os.path.join(objdir, os.path.splitext(os.path.basename(s))[0] + ".o") for s in srcs]
+
+        def cc(pair):
+            src, obj = pair
+            return _run([NVCC] + NVCC_FLAGS + list(extra_flags) + ["-c", "-o", obj, src], f"build_cuda{variant}_{os.path.basename(src)}.log")
+        with ThreadPoolExecutor(len(srcs)) as ex:
+            logs = list(ex.map(cc, zip(srcs, objs)))
+        with open(os.path.join(LIB, f"build_cuda{variant}.log"), "w") as fh:      # one combined ptxas -v log, as before
+            for r in logs:
+                fh.write(r.stdout + r.stderr)
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target] + objs + ["-ldl"], f"link_cuda{variant}.log")
     return target
 
 

@@ -1,5 +1,6 @@
 // main.cpp -- `nori <scene.xml>` command line (ref: src/main.cpp:150-246).  --no-gui / --threads are accepted for
-// compatibility and ignored (there is no GUI and no TBB on this path); --device N selects the GPU.
+// compatibility and ignored (there is no GUI and no TBB on this path); --device N selects the GPU, --gpus N
+// renders on N devices (tiles sharded tile_id % N, finished ImageBlocks gathered over NCCL, merged on the first device).
 #include <cstring>
 #include "nori/parser.h"
 #include "nori/render.h"
@@ -8,7 +9,7 @@ using namespace nori;
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N] [--lbvh]" << endl;
+        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N] [--gpus N] [--lbvh]" << endl;
         return -1;
     }
     std::string sceneName;
@@ -21,6 +22,9 @@ int main(int argc, char **argv) {
         } else if (token == "--no-gui") {
         } else if (token == "--lbvh") {
             opt.deviceBuilder = true;   // GPU-built hierarchy (fast build, slightly slower render)
+        } else if (token == "--gpus") {
+            if (i + 1 >= argc || atoi(argv[i + 1]) < 1) { cerr << "\"--gpus\" expects a positive integer following it." << endl; return -1; }
+            opt.gpus = atoi(argv[++i]);   // devices device .. device+N-1 render tile shards; blocks gathered over NCCL
         } else if (token == "--device") {
             if (i + 1 >= argc) { cerr << "\"--device\" expects an integer following it." << endl; return -1; }
             opt.device = atoi(argv[++i]);

@@ -10,7 +10,8 @@ struct nb_bsdf_desc;
 NORI_NAMESPACE_BEGIN
 
 struct RenderOptions {
-    int device = 0;            // CUDA device of this process
+    int device = 0;            // CUDA device of this process (first device of the group when gpus > 1)
+    int gpus = 1;              // devices driven by this process: tiles sharded tile_id % gpus, ONE NCCL gather per frame (nb_create_multi)
     int tileRank = 0, tileRanks = 1;   // tile shard (multi-GPU: one process per GPU)
     bool quiet = false;
     bool deviceBuilder = false;        // build the hierarchy on the GPU (LBVH) instead of the host SAH builder

@@ -73,8 +73,16 @@ nb_integrator_desc describeIntegrator(const Integrator *integ) {
 void describeBSDF(const BSDF *bsdf, nb_bsdf_desc *out) { *out = describeBSDF(bsdf); }
 
 nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const RenderOptions &opt) {
-    nb_ctx *ctx = nb_create(opt.device);
-    if (!ctx) throwLast("nb_create");
+    nb_ctx *ctx = nullptr;
+    if (opt.gpus > 1) {        // N devices behind the same calls (ref: the TBB tile loop + merge, src/main.cpp:85-113)
+        std::vector<int> devices;
+        for (int i = 0; i < opt.gpus; ++i) devices.push_back(opt.device + i);
+        ctx = nb_create_multi(devices.data(), opt.gpus);
+        if (!ctx) throwLast("nb_create_multi");
+    } else {
+        ctx = nb_create(opt.device);
+        if (!ctx) throwLast("nb_create");
+    }
     try {
         if (opt.deviceBuilder && nb_set_option(ctx, "builder", 1)) throwLast("nb_set_option");
         for (const Mesh *mesh : scene->getMeshes()) {   // Scene::addChild(mesh) -> Accel::addMesh (ref: src/scene.cpp:48-53)
@@ -105,7 +113,7 @@ nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const Rend
             const float p3[3] = { pos.x(), pos.y(), pos.z() }, e3[3] = { en.r(), en.g(), en.b() };
             if (nb_set_point_light(ctx, p3, e3)) throwLast("nb_set_point_light");
         }
-        if (nb_set_tiles(ctx, opt.tileRank, opt.tileRanks)) throwLast("nb_set_tiles");
+        if (opt.gpus <= 1 && nb_set_tiles(ctx, opt.tileRank, opt.tileRanks)) throwLast("nb_set_tiles");
     } catch (...) {
         nb_destroy(ctx);
         throw;
@@ -206,6 +214,17 @@ int nori_host_mesh(void *scene_, int i, uint32_t *nv, uint32_t *nf, const float 
 }
 
 /// Renders through the C-ABI (GPU required).  film: (H+2b) x (W+2b) x 4 floats.
+int nori_host_render_gpus(void *scene_, int device, int gpus, float *film, nb_stats *stats) {
+    try {
+        nori::Scene *scene = static_cast<nori::Scene *>(scene_);
+        nori::ImageBlock blk(scene->getCamera()->getOutputSize(), scene->getCamera()->getReconstructionFilter());
+        nori::RenderOptions opt; opt.device = device; opt.gpus = gpus; opt.quiet = true;
+        nori::renderScene(scene, blk, opt, stats);
+        std::memcpy(film, blk.data(), sizeof(float) * 4 * (size_t) blk.rows() * blk.cols());
+        return 0;
+    } catch (const std::exception &e) { g_host_err = e.what(); return 1; }
+}
+
 int nori_host_render(void *scene_, int device, int tile_rank, int tile_ranks, float *film, nb_stats *stats) {
     try {
         nori::Scene *scene = static_cast<nori::Scene *>(scene_);

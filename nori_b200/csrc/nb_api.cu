@@ -2,7 +2,7 @@
 //
 // No CPU fallback exists in this file: every entry point either runs the sm_100a kernels or fails with an
 // error.  The oracle (oracle/) is never linked or called from here.
-#include "../../include/nori_b200.h"
+#include "nb_ctx.h"
 #include "nb_bvh.h"
 #include "nb_kernels.cuh"
 #include "nb_lbvh.cuh"
@@ -14,75 +14,24 @@
 #include <string>
 #include <vector>
 
-namespace {
-
+namespace nbi {
 thread_local std::string g_err;
-
 int fail(const char *fmt, ...) {
     char buf[1024];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
     g_err = buf;
     return 1;
 }
+}  // namespace nbi
+using nbi::fail; using nbi::HostMesh; using nbi::DevBuf;
 
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
-
-struct HostMesh {
-    std::vector<float> V, N, UV;
-    std::vector<uint32_t> F;
-    uint32_t nv = 0, nf = 0;
-    nb_bsdf_desc bsdf;
-    nb_emitter_desc emitter;
-};
-
-template <typename T>
-struct DevBuf {
-    T *d = nullptr; T *h = nullptr; size_t n = 0;   // device + pinned host mirror
-    void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = nullptr; h = nullptr; n = 0; }
-    cudaError_t alloc(size_t count) {
-        release(); n = count;
-        size_t bytes = sizeof(T) * (count ? count : 1);
-        cudaError_t e = cudaMalloc(&d, bytes); if (e != cudaSuccess) return e;
-        return cudaMallocHost(&h, bytes);
-    }
-    size_t bytes() const { return sizeof(T) * n; }
-};
-
-}  // namespace
-
-struct nb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-    int sm_count = 0;
-    std::vector<HostMesh> meshes;
-    // scene tables (device + pinned mirrors)
-    DevBuf<float4> nodes, tris, verts, normals;
-    DevBuf<float2> uvs;
-    DevBuf<uint4> faces;
-    DevBuf<nb::DevMesh> dmeshes;
-    DevBuf<float> cdf;
-    DevBuf<int32_t> emitters;
-    uint32_t n_nodes = 0, n_prims = 0, top_nodes = 0; int bvh_depth = 0; bool built = false;
-    double build_seconds = 0;
-    // camera / film / sampler / integrator
-    float s2c[16], c2w[16]; int W = 0, H = 0; float nearClip = 1e-4f, farClip = 1e4f; bool have_camera = false;
-    float ftable[33]; float fradius = 2.0f; int border = 2;
-    uint32_t spp = 1; int seed_mode = NB_SEED_PER_SAMPLE; uint64_t seed = 0;
-    nb_integrator_desc integ = { NB_INT_NORMALS, 3, 0, 0 };
-    float light_pos[3] = { 0, 0, 0 }, light_energy[3] = { 0, 0, 0 }; bool have_light = false;
-    int tile_rank = 0, tile_nranks = 1;
-    // work buffers
-    float4 *blocks = nullptr; size_t blocks_cap = 0;
-    float4 *film = nullptr; size_t film_cap = 0;
-    unsigned long long *counters = nullptr;          // 8 x u64 device
-    unsigned long long *counters_h = nullptr;        // pinned
-    // options
-    int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 0, opt_count = 0, opt_max_leaf = 3,
-            opt_bfs_nodes = 2048, opt_builder = 0, opt_tail = 0, opt_engine = 0, opt_occ_mb = 1024, opt_occ_tail = 20;
-    float4 *occ_queue = nullptr; size_t occ_cap = 0;   // deferred-occlusion engine: ray queue (rays)
-    int builder_used = 0;   // 0 host SAH, 1 device LBVH
-};
+namespace nbm {     // nb_multi.inl (end of this file)
+int replicate_scene(nb_ctx *c, bool with_header);
+int render_group(nb_ctx *c, float4 *film, cudaStream_t s0, nb_stats *st);
+void release_group(nb_ctx *c);
+bool grouped(const nb_ctx *c);
+int render_group_stats(nb_ctx *c, cudaStream_t s0, nb_stats *st);
+}
 
 namespace {
 
@@ -359,6 +308,7 @@ int finish_stats(nb_ctx *c, cudaStream_t s, nb_stats *st, int extra_launches) {
     CK(cudaMemcpyAsync(c->counters_h, c->counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(c->ev[3], s));
     CK(cudaStreamSynchronize(s));
+    if (c->counters_h[6] >> 63) return fail("device watchdog fired: a persistent loop of an experimental engine did not terminate (results invalid)");
     if (st) {
         st->rays = c->counters_h[1]; st->node_visits = c->counters_h[2]; st->tri_tests = c->counters_h[3];
         st->hits_shaded = c->counters_h[4];
@@ -427,7 +377,7 @@ int build_lbvh_device(nb_ctx *c, size_t nf, float pad, const float clo[3], const
 
 extern "C" {
 
-const char *nb_last_error(void) { return g_err.c_str(); }
+const char *nb_last_error(void) { return nbi::g_err.c_str(); }
 int nb_abi_version(void) { return NB_ABI_VERSION; }
 
 nb_ctx *nb_create(int device) {
@@ -458,7 +408,10 @@ nb_ctx *nb_create(int device) {
 
 void nb_destroy(nb_ctx *c) {
     if (!c) return;
+    for (nb_ctx *f : c->followers) { f->leader = nullptr; nb_destroy(f); }
+    c->followers.clear();
     cudaSetDevice(c->device);
+    nbm::release_group(c);
     c->nodes.release(); c->tris.release(); c->verts.release(); c->normals.release(); c->uvs.release(); c->faces.release();
     c->dmeshes.release(); c->cdf.release(); c->emitters.release();
     if (c->blocks) cudaFree(c->blocks);
@@ -497,12 +450,15 @@ int nb_add_mesh(nb_ctx *c, const float *V, uint32_t nv, const float *N, const fl
     return (int) c->meshes.size() - 1;
 }
 
-int nb_clear_meshes(nb_ctx *c) { if (!c) return fail("null context"); c->meshes.clear(); c->built = false; return 0; }
-
-int nb_upload_scene(nb_ctx *c) {
+int nb_clear_meshes(nb_ctx *c) {
     if (!c) return fail("null context");
-    if (!c->built) return fail("nb_build_accel has not been called");
-    if (ensure_device(c)) return 1;
+    c->meshes.clear(); c->built = false;
+    c->have_light = false;          // a new scene starts without the previous scene's point light
+    for (nb_ctx *f : c->followers) { f->built = false; f->have_light = false; }
+    return 0;
+}
+
+static int upload_local(nb_ctx *c) {
     cudaStream_t s = c->stream;
 #define UP(buf) CK(cudaMemcpyAsync(buf.d, buf.h, buf.bytes(), cudaMemcpyHostToDevice, s))
     UP(c->nodes); UP(c->tris); UP(c->verts); UP(c->normals); UP(c->uvs); UP(c->faces); UP(c->dmeshes); UP(c->cdf); UP(c->emitters);
@@ -511,9 +467,31 @@ int nb_upload_scene(nb_ctx *c) {
     return 0;
 }
 
+int nb_upload_scene(nb_ctx *c) {
+    if (!c) return fail("null context");
+    if (c->leader) return fail("nb_upload_scene: call it on the group's leader context");
+    if (!c->built) return fail("nb_build_accel has not been called");
+    if (ensure_device(c)) return 1;
+    // ONE copy crosses PCIe; the other ranks of a group receive it over NVLink (ncclBroadcast)
+    if (c->comm_rank == 0 && upload_local(c)) return 1;
+    if (nbm::grouped(c)) return nbm::replicate_scene(c, false);
+    return 0;
+}
+
+static int build_accel_local(nb_ctx *c);
+
 int nb_build_accel(nb_ctx *c) {
     if (!c) return fail("null context");
+    if (c->leader) return fail("nb_build_accel: call it on the group's leader context");
     if (ensure_device(c)) return 1;
+    // In a group the hierarchy is built ONCE, by rank 0, and replicated over NVLink; the other ranks only receive.
+    if (nbm::grouped(c) && c->comm_rank != 0) return nbm::replicate_scene(c, true);
+    if (build_accel_local(c)) return 1;
+    if (nbm::grouped(c)) return nbm::replicate_scene(c, true);
+    return 0;
+}
+
+static int build_accel_local(nb_ctx *c) {
     size_t nv = 0, nf = 0, ncdf = 0, nem = 0;
     for (auto &m : c->meshes) { nv += m.nv; nf += m.nf; if (m.emitter.type == NB_EMITTER_AREA) { ncdf += m.nf + 1; nem++; } }
     if (nf >= (1u << 28)) return fail("too many triangles (%zu)", nf);
@@ -599,7 +577,7 @@ int nb_build_accel(nb_ctx *c) {
     memcpy(c->nodes.h, out.nodes.data(), out.nodes.size() * sizeof(float));
     if (!out.tris.empty()) memcpy(c->tris.h, out.tris.data(), out.tris.size() * sizeof(float));
     c->built = true;
-    return nb_upload_scene(c);
+    return upload_local(c);
 }
 
 int nb_build_stats(nb_ctx *c, double *seconds, int *builder) {
@@ -616,6 +594,7 @@ int nb_set_camera(nb_ctx *c, const float s2c[16], const float c2w[16], int width
     if (width <= 0 || height <= 0 || width > 32767 || height > 32767) return fail("invalid output size %dx%d", width, height);
     memcpy(c->s2c, s2c, sizeof c->s2c); memcpy(c->c2w, c2w, sizeof c->c2w);
     c->W = width; c->H = height; c->nearClip = nearClip; c->farClip = farClip; c->have_camera = true;
+    for (nb_ctx *f : c->followers) if (nb_set_camera(f, s2c, c2w, width, height, nearClip, farClip)) return 1;
     return 0;
 }
 
@@ -627,6 +606,7 @@ int nb_set_filter(nb_ctx *c, const float table[NB_FILTER_RESOLUTION + 1], float 
     if (border > 8) return fail("filter radius %f too large", radius);
     memcpy(c->ftable, table, sizeof c->ftable);
     c->fradius = radius; c->border = border;
+    for (nb_ctx *f : c->followers) if (nb_set_filter(f, table, radius)) return 1;
     return 0;
 }
 
@@ -635,6 +615,7 @@ int nb_set_sampler(nb_ctx *c, uint32_t spp, int seed_mode, uint64_t seed) {
     if (spp == 0) return fail("sampleCount must be >= 1");
     if (seed_mode != NB_SEED_PER_SAMPLE && seed_mode != NB_SEED_PER_BLOCK) return fail("unknown seed mode %d", seed_mode);
     c->spp = spp; c->seed_mode = seed_mode; c->seed = seed;
+    for (nb_ctx *f : c->followers) if (nb_set_sampler(f, spp, seed_mode, seed)) return 1;
     return 0;
 }
 
@@ -642,6 +623,7 @@ int nb_set_integrator(nb_ctx *c, const nb_integrator_desc *d) {
     if (!c || !d) return fail("null argument");
     if (d->type < NB_INT_NORMALS || d->type > NB_INT_SIMPLE) return fail("unsupported integrator type %d (no CPU fallback)", d->type);
     c->integ = *d;
+    for (nb_ctx *f : c->followers) if (nb_set_integrator(f, d)) return 1;
     return 0;
 }
 
@@ -649,12 +631,15 @@ int nb_set_point_light(nb_ctx *c, const float position[3], const float energy[3]
     if (!c || !position || !energy) return fail("null argument");
     memcpy(c->light_pos, position, sizeof c->light_pos); memcpy(c->light_energy, energy, sizeof c->light_energy);
     c->have_light = true;
+    for (nb_ctx *f : c->followers) if (nb_set_point_light(f, position, energy)) return 1;
     return 0;
 }
 
 int nb_set_tiles(nb_ctx *c, int rank, int nranks) {
     if (!c) return fail("null context");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("invalid tile shard (%d of %d)", rank, nranks);
+    if (nbm::grouped(c) && (rank != c->comm_rank || nranks != c->comm_nranks))
+        return fail("nb_set_tiles: a context in a %d-GPU group renders shard (%d, %d); the group owns the tile assignment", c->comm_nranks, c->comm_rank, c->comm_nranks);
     c->tile_rank = rank; c->tile_nranks = nranks;
     return 0;
 }
@@ -706,26 +691,51 @@ int nb_merge_all_blocks_device(nb_ctx *c, const float *blocks_dev, int nranks, i
 int nb_render_device(nb_ctx *c, float *film_dev, void *stream, nb_stats *st) {
     if (!c || !film_dev) return fail("null argument");
     cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;
+    if (nbm::grouped(c)) {
+        if (c->leader) return fail("nb_render_device: call it on the group's leader context");
+        if (ensure_device(c)) return 1;
+        return nbm::render_group(c, reinterpret_cast<float4 *>(film_dev), s, st);
+    }
     int n_tiles = 0;
     if (render_tiles(c, nullptr, s, st, &n_tiles)) return 1;
     const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
     CK(cudaMemsetAsync(film_dev, 0, sizeof(float4) * film_elems, s));
     if (merge(c, c->blocks, n_tiles, c->tile_rank, c->tile_nranks, reinterpret_cast<float4 *>(film_dev), s)) return 1;
+    if (!st) return 0;               // fire and forget: no counter read-back, no host synchronisation
     return finish_stats(c, s, st, n_tiles > 0 ? 1 : 0);
 }
 
+int nb_last_kernel_ms(nb_ctx *c, double *ms) {
+    if (!c || !ms) return fail("null argument");
+    if (ensure_device(c)) return 1;
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->ev[1], c->ev[2]));      // fails with cudaErrorNotReady while the render is still running
+    *ms = f;
+    return 0;
+}
+
 int nb_render(nb_ctx *c, float *film_host, nb_stats *st) {
-    if (!c || !film_host) return fail("null argument");
+    if (!c || (!film_host && !(nbm::grouped(c) && c->comm_rank != 0))) return fail("null argument");
     if (ensure_device(c)) return 1;
     const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
     if (film_elems > c->film_cap) {
         if (c->film) cudaFree(c->film);
-    if (c->occ_queue) cudaFree(c->occ_queue);
         c->film = nullptr; c->film_cap = 0;
         CK(cudaMalloc(&c->film, sizeof(float4) * (film_elems ? film_elems : 1)));
         c->film_cap = film_elems;
     }
     cudaStream_t s = c->stream;
+    if (nbm::grouped(c)) {
+        // N devices behind the same call: tiles sharded tile_id % N, ONE NCCL gather of the finished blocks, ONE merge
+        if (c->leader) return fail("nb_render: call it on the group's leader context");
+        nb_stats tmp; if (!st) st = &tmp;
+        if (nbm::render_group(c, c->film, s, nullptr)) return 1;
+        if (c->comm_rank == 0) CK(cudaMemcpyAsync(film_host, c->film, sizeof(float4) * film_elems, cudaMemcpyDeviceToHost, s));
+        // statistics after the film copy is queued: one synchronisation for the whole frame
+        if (nbm::render_group_stats(c, s, st)) return 1;
+        st->d2h_bytes = c->comm_rank == 0 ? sizeof(float4) * film_elems : 0; st->h2d_bytes = sizeof(nb::RenderParams);
+        return 0;
+    }
     int n_tiles = 0;
     if (render_tiles(c, nullptr, s, st, &n_tiles)) return 1;
     CK(cudaMemsetAsync(c->film, 0, sizeof(float4) * film_elems, s));
@@ -920,6 +930,7 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     else if (k == "bfs_nodes") { c->opt_bfs_nodes = value; c->built = false; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail("builder must be 0 (host SAH) or 1 (device LBVH)"); c->opt_builder = value; c->built = false; }
     else return fail("unknown option \"%s\"", key);
+    for (nb_ctx *f : c->followers) if (nb_set_option(f, key, value)) return 1;
     return 0;
 }
 
@@ -940,3 +951,5 @@ int nb_scene_info(nb_ctx *c, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_
 }
 
 }  // extern "C"
+
+#include "nb_multi.inl"

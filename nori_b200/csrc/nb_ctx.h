@@ -1,0 +1,80 @@
+// nb_ctx.h -- private definition of nb_ctx, shared by the translation units of libnori_b200.so (nb_api.cu: kernels and
+// single-device entry points; nb_multi.cu: NCCL communicators and the multi-device render).  Not part of the C-ABI.
+#pragma once
+#include "../../include/nori_b200.h"
+#include "nb_device.cuh"
+
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+namespace nbi {
+
+int fail(const char *fmt, ...);     // sets the thread-local message of nb_last_error(), returns 1
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return nbi::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct HostMesh {
+    std::vector<float> V, N, UV;
+    std::vector<uint32_t> F;
+    uint32_t nv = 0, nf = 0;
+    nb_bsdf_desc bsdf;
+    nb_emitter_desc emitter;
+};
+
+template <typename T>
+struct DevBuf {
+    T *d = nullptr; T *h = nullptr; size_t n = 0;   // device + pinned host mirror (h stays null for device-only buffers)
+    void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = nullptr; h = nullptr; n = 0; }
+    cudaError_t alloc(size_t count, bool with_host = true) {
+        release(); n = count;
+        size_t bytes = sizeof(T) * (count ? count : 1);
+        cudaError_t e = cudaMalloc(&d, bytes); if (e != cudaSuccess) return e;
+        return with_host ? cudaMallocHost(&h, bytes) : cudaSuccess;
+    }
+    size_t bytes() const { return sizeof(T) * n; }
+};
+
+}  // namespace nbi
+
+struct nb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    int sm_count = 0;
+    std::vector<nbi::HostMesh> meshes;
+    // scene tables (device + pinned mirrors)
+    nbi::DevBuf<float4> nodes, tris, verts, normals;
+    nbi::DevBuf<float2> uvs;
+    nbi::DevBuf<uint4> faces;
+    nbi::DevBuf<nb::DevMesh> dmeshes;
+    nbi::DevBuf<float> cdf;
+    nbi::DevBuf<int32_t> emitters;
+    uint32_t n_nodes = 0, n_prims = 0, top_nodes = 0; int bvh_depth = 0; bool built = false;
+    double build_seconds = 0;
+    // camera / film / sampler / integrator
+    float s2c[16], c2w[16]; int W = 0, H = 0; float nearClip = 1e-4f, farClip = 1e4f; bool have_camera = false;
+    float ftable[33]; float fradius = 2.0f; int border = 2;
+    uint32_t spp = 1; int seed_mode = NB_SEED_PER_SAMPLE; uint64_t seed = 0;
+    nb_integrator_desc integ = { NB_INT_NORMALS, 3, 0, 0 };
+    float light_pos[3] = { 0, 0, 0 }, light_energy[3] = { 0, 0, 0 }; bool have_light = false;
+    int tile_rank = 0, tile_nranks = 1;
+    // work buffers
+    float4 *blocks = nullptr; size_t blocks_cap = 0;
+    float4 *film = nullptr; size_t film_cap = 0;
+    unsigned long long *counters = nullptr;          // 8 x u64 device
+    unsigned long long *counters_h = nullptr;        // pinned
+    // options
+    int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 0, opt_count = 0, opt_max_leaf = 3,
+            opt_bfs_nodes = 2048, opt_builder = 0, opt_tail = 0, opt_engine = 0, opt_occ_mb = 1024, opt_occ_tail = 20;
+    float4 *occ_queue = nullptr; size_t occ_cap = 0;   // deferred-occlusion engine: ray queue (rays)
+    int builder_used = 0;   // 0 host SAH, 1 device LBVH
+    // ---- multi-GPU (nb_multi.inl)
+    std::vector<nb_ctx *> followers;   // nb_create_multi: the contexts on the other devices (owned by this leader)
+    nb_ctx *leader = nullptr;          // set on followers
+    void *comm = nullptr;              // ncclComm_t of this context (single-process group or nb_comm_init_rank)
+    int comm_rank = 0, comm_nranks = 1;
+    float4 *gather = nullptr; size_t gather_cap = 0;   // rank 0: blocks of all ranks, [nranks][n_max][edge][edge]
+    float4 *send_blocks = nullptr; size_t send_cap = 0; // ranks > 0: own blocks padded to n_max tiles
+    nb_stats last_st = {};             // statistics of this context's last render inside a group
+};

@@ -52,6 +52,9 @@ namespace nb {
 #ifndef NB_SPLAT_HOIST
 #define NB_SPLAT_HOIST 1
 #endif
+#ifndef NB_WATCHDOG_CYCLES
+#define NB_WATCHDOG_CYCLES 40000000000LL   // ~20 s at 1.9 GHz
+#endif
 constexpr int kStack = 64;          // builder guarantees depth < 64 (nb_bvh.cpp)
 constexpr int kBlockEdgeMax = 32 + 2 * 8;
 
@@ -126,6 +129,15 @@ __device__ __forceinline__ void trav_begin(const Ray &r, Trav &t) {
     t.node = 0; t.sp = 0;
 }
 
+#ifndef NB_LDG256
+#define NB_LDG256 0
+#endif
+// 32 bytes (two float4) through the read-only path with ONE instruction; p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 template <bool TMA_TOP>
 __device__ __forceinline__ float4 ld_node(const SceneDev &sc, const float4 *snodes, int smem_nodes, int node, int k) {
     if (TMA_TOP && node < smem_nodes) return snodes[node * 4 + k];
@@ -187,10 +199,22 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
     while (node != kDone || parked != 0) {
         // ---- inner nodes
         while (node >= 0 && node != kDone) {
+#if NB_LDG256
+            // sm_100a has 256-bit global loads (SASS LDG.E.ENL2.256): a 64 B node is two load instructions instead of
+            // four -- half the L1 wavefronts of a lane-divergent node fetch, which is what bounds the walk
+            float4 n0, n1, n2, n3;
+            if (TMA_TOP && node < smem_nodes) {
+                n0 = snodes[node * 4 + 0]; n1 = snodes[node * 4 + 1]; n2 = snodes[node * 4 + 2]; n3 = snodes[node * 4 + 3];
+            } else {
+                ldg256(sc.nodes + (size_t) node * 4, n0, n1);
+                ldg256(sc.nodes + (size_t) node * 4 + 2, n2, n3);
+            }
+#else
             const float4 n0 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 0);
             const float4 n1 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 1);
             const float4 n2 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 2);
             const float4 n3 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 3);
+#endif
             if (COUNT) n_nodes++;
             // slab tests (explicit fma: may only cull; boxes are padded by the builder)
             float c0lox = __fmaf_rn(n0.x, t.idx, -t.oodx), c0hix = __fmaf_rn(n0.y, t.idx, -t.oodx);
@@ -705,7 +729,13 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
 
+#if NB_TAIL_CUT || NB_DEFER_SHADOW
+    const long long wd_t0 = clock64();          // experimental engines: a bug must fail (counters[6] bit 63), never hang the GPU
+#endif
     for (;;) {
+#if NB_TAIL_CUT || NB_DEFER_SHADOW
+        if (__any_sync(0xffffffffu, clock64() - wd_t0 > NB_WATCHDOG_CYCLES)) { if (lane == 0) atomicOr(&P.counters[6], 1ull << 63); break; }
+#endif
         // ---- shading phase (lock step: every lane's ray is finished here)
         if (ps.stage != ST_IDLE && traced && (!NB_TAIL_CUT || tr.node == kDone)) {
             const bool finished = shade<INTEG>(P, ps, ray, tr, n_hits);
@@ -905,7 +935,9 @@ __global__ void __launch_bounds__(128, NB_MIN_BLOCKS) occlusion_kernel(const __g
     bool active = false, exhausted = false;
     unsigned long long n_in = P.counters[7];
     if (n_in > (unsigned long long) P.occ_capacity) n_in = P.occ_capacity;
+    const long long wd_t0 = clock64();
     for (;;) {
+        if (__any_sync(0xffffffffu, clock64() - wd_t0 > NB_WATCHDOG_CYCLES)) { if (lane == 0) atomicOr(&P.counters[6], 1ull << 63); break; }
         // ---- refill (all 32 lanes are converged here)
         const unsigned idle_mask = __ballot_sync(0xffffffffu, !active);
         if (idle_mask != 0u && !exhausted) {

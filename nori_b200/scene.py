@@ -382,10 +382,15 @@ def config_bunny(spp=1, seed_mode=SEED_PER_BLOCK) -> Scene:
 _AJAX_CAM = dict(origin=[-65.6055, 47.5762, 24.3583], target=[-64.8161, 47.2211, 23.8576], up=[0.299858, 0.934836, -0.190177])
 
 
-def config_ajax_ao(width=800, height=600, spp=64, levels=4) -> Scene:
+def empty_mesh() -> Mesh:
+    """Placeholder geometry for the ranks of a multi-GPU group that receive the scene arrays from rank 0 over NVLink."""
+    return Mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), name="(replicated from rank 0)")
+
+
+def config_ajax_ao(width=800, height=600, spp=64, levels=4, geometry=True) -> Scene:
     """configs[1]: Ajax(stand-in) ambient occlusion, camera of ref scenes/pa3/ajax-ao.xml:19-23, fov 30."""
     cam = Camera(lookat(**_AJAX_CAM).astype(np.float32), 30.0, width, height)
-    return Scene([ajax_standin(levels)], cam, INT_AO, spp, name=f"ajax-ao-{width}x{height}x{spp}")
+    return Scene([ajax_standin(levels) if geometry else empty_mesh()], cam, INT_AO, spp, name=f"ajax-ao-{width}x{height}x{spp}")
 
 
 def config_cbox(width=512, height=512, spp=256, integrator=INT_PATH_MIS) -> Scene:
@@ -403,20 +408,20 @@ def config_cbox(width=512, height=512, spp=256, integrator=INT_PATH_MIS) -> Scen
     return Scene(meshes, cam, integrator, spp, name=f"cbox-{width}x{height}x{spp}")
 
 
-def config_ajax_microfacet(width=768, height=768, spp=1024, levels=4, integrator=INT_PATH_MIS) -> Scene:
+def config_ajax_microfacet(width=768, height=768, spp=1024, levels=4, integrator=INT_PATH_MIS, geometry=True) -> Scene:
     """configs[3]: ref scenes/pa5/ajax/ajax-rough.xml:14-28 -- microfacet intIOR 1.7, kd .2 .2 .4, alpha .28; light quad radiance 20."""
     cam = Camera(lookat(**_AJAX_CAM).astype(np.float32), 30.0, width, height)
     meshes = [
-        with_(ajax_standin(levels), microfacet((0.2, 0.2, 0.4), 0.28, 1.7)),
+        with_(ajax_standin(levels) if geometry else empty_mesh(), microfacet((0.2, 0.2, 0.4), 0.28, 1.7)),
         with_(golden_mesh("ajax_light"), diffuse(), radiance=(20, 20, 20)),
     ]
     return Scene(meshes, cam, integrator, spp, name=f"ajax-rough-{width}x{height}x{spp}")
 
 
-def config_random_tris(n=10_000_000, width=1920, height=1080, spp=1, integrator=INT_AO, s=0.01) -> Scene:
+def config_random_tris(n=10_000_000, width=1920, height=1080, spp=1, integrator=INT_AO, s=0.01, geometry=True) -> Scene:
     """configs[4]: synthetic n random triangles, camera at (0,0,4) looking at the origin, fov 40."""
     cam = Camera(lookat([0, 0, 4], [0, 0, 0], [0, 1, 0]).astype(np.float32), 40.0, width, height)
-    return Scene([random_triangles(n, s)], cam, integrator, spp, name=f"random{n}-{width}x{height}x{spp}")
+    return Scene([random_triangles(n, s) if geometry else empty_mesh()], cam, integrator, spp, name=f"random{n}-{width}x{height}x{spp}")
 
 
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_sizes():
     L = abi.lib()
-    assert L.nb_abi_version() == 1
+    assert L.nb_abi_version() == 2      # 2: N GPUs behind the boundary (nb_create_multi, nb_comm_*, nb_render_gather)
     assert C.sizeof(abi.BsdfDesc) == 32
     assert C.sizeof(abi.EmitterDesc) == 16
     assert C.sizeof(abi.IntegratorDesc) == 16
@@ -37,6 +37,8 @@ def test_no_cpu_fallback_without_gpu():
     assert b"no CUDA device" in L.nb_last_error()
     with pytest.raises(abi.NoriError):
         abi.Context(0)
+    with pytest.raises(abi.NoriError, match="no CUDA device"):
+        abi.Context([0, 1])            # the multi-GPU constructor fails the same way
 
 
 def test_product_does_not_import_oracle():

@@ -2,10 +2,7 @@
 (NB_INT_SIMPLE, ref: scenes/pa3/ajax-simple.xml:8-11), nb_li_samples and the `ttest` scene object built on it
 (ref: src/ttest.cpp:140-176).
 
-Added after round 1's GPU minutes were spent: the device code compiles for sm_100a and mirrors oracle.c operation for
-operation, but has NOT yet run on hardware.  The tests are therefore xfail(strict=False) -- they report XPASS when they
-pass -- and live in the last-collected file so that nothing runs after them.  Remove the marks after their first green
-run on a B200.
+First hardware run: the driver's round-1 GPU tier (GPUTEST_r01.json, 13 XPASS).  They are plain tests since round 2.
 """
 import os
 import subprocess
@@ -16,7 +13,7 @@ import pytest
 from nori_b200 import abi, host
 from nori_b200 import scene as S
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (added without GPU budget)")]
+pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 

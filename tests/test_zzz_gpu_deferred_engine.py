@@ -1,7 +1,7 @@
 """GPU parity of the deferred-occlusion engine (nori_b200/csrc/nb_wavefront.cu, nb_set_option("engine", 1)).
 
 Written after round 1's GPU minutes were spent and never run on hardware.  Unlike the single-loop kernels in
-test_zz_gpu_late_entry_points.py this engine has persistent warps with resumable walks and a device-side queue, so a
+test_gpu_entry_points.py this engine has persistent warps with resumable walks and a device-side queue, so a
 mistake could hang rather than fail: the tests are SKIPPED unless NB_RUN_UNVALIDATED=1 (tools/round2_experiments.sh sets
 it and wraps the run in a timeout).  Remove the gate after the first green run on a B200.
 """
@@ -12,7 +12,7 @@ import pytest
 
 from nori_b200 import abi
 from nori_b200 import scene as S
-from tests.test_zz_gpu_late_entry_points import simple_scene
+from tests.test_gpu_entry_points import simple_scene
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("NB_RUN_UNVALIDATED") != "1", reason="never run on hardware: set NB_RUN_UNVALIDATED=1")]

@@ -10,7 +10,7 @@ tails = [int(x) for x in os.environ.get("TAILS", "0 4 8 12 16").split()]
 for wl in sys.argv[1:] or ["ajax-ao", "cbox-mis"]:
     a = A()
     if wl == "ajax-rough": a.spp = 64
-    sc = bench.WORKLOADS[wl](a)
+    sc = bench.build_scene(wl, a)
     ctx = abi.Context(0); ctx.load(sc)
     ref = None
     for t in tails:
