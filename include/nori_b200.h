@@ -122,6 +122,12 @@ int nb_build_accel(nb_ctx *);
  * 1 = device LBVH (nb_set_option(ctx, "builder", 1); Morton sort + Karras radix tree on the GPU, ~100x faster to
  * build, lower tree quality).  Results are identical with either tree. */
 int nb_build_stats(nb_ctx *, double *seconds, int *builder);
+/* On-disk cache of the built hierarchy (host SAH builder): with a path set, nb_build_accel first looks for a file whose key
+ * -- a 64-bit hash of every vertex and index the builder reads, the build parameters and the layout version -- matches, and
+ * loads nodes + leaf-ordered triangles from it instead of building; otherwise it builds and writes the file (silently
+ * skipped if the directory is read-only).  NULL or "" disables.  nb_accel_cache_hit: 1 if the last build was served by it. */
+int nb_set_accel_cache(nb_ctx *, const char *path);
+int nb_accel_cache_hit(nb_ctx *);
 /* Re-uploads the already built scene arrays from pinned host memory (used to time host->device traffic). */
 int nb_upload_scene(nb_ctx *);
 
@@ -202,6 +208,12 @@ int nb_intersect_full(nb_ctx *, const nb_ray *rays, uint64_t n, float *out16);
 /* Film normalisation: ImageBlock::toBitmap (ref: src/block.cpp:45-51, include/nori/color.h:100-105). HOST buffers. */
 int nb_film_to_rgb(nb_ctx *, const float *film_host, float *rgb_host);
 
+/* Output path on the device: normalisation (ImageBlock::toBitmap, ref: src/block.cpp:45-51), sRGB tonemap
+ * (Color3f::toSRGB, ref: src/common.cpp:166-180) and 8-bit quantisation (ref: src/bitmap.cpp:100-110) of the film the last
+ * nb_render left on the device, in one kernel; rgb8_host receives W x H x 3 bytes, ready for the PNG writer.  The bytes
+ * equal the host loop's (both sides evaluate x^(1/2.4) with the same polynomials). */
+int nb_last_film_to_srgb8(nb_ctx *, uint8_t *rgb8_host);
+
 /* Tuning knobs (optional; sane defaults): key/value, see DESIGN.md section 6.  Unknown key -> error. */
 int nb_set_option(nb_ctx *, const char *key, int64_t value);
 /* Raw device counters of the last call (diagnostics; meaningful with option "count" = 1): [1] rays, [2] node visits,
@@ -213,6 +225,10 @@ int nb_debug_counters(nb_ctx *, uint64_t out[8]);
  * outputs to size the arrays (capacities in floats).  Returns 0, 1 (bad argument) or 2 (capacity too small). */
 int nb_debug_build_bvh(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes,
                        float *nodes_out, uint64_t nodes_cap, float *tris_out, uint64_t tris_cap, uint32_t info[4]);
+/* Host-only diagnostic of the hierarchy cache: key -> load, else build + save, exactly as nb_build_accel does with
+ * nb_set_accel_cache.  info = { nodes, leaf triangles, top nodes, depth, hit (0/1) }. */
+int nb_debug_bvh_cache(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes, const char *path,
+                       float *nodes_out, uint64_t nodes_cap, float *tris_out, uint64_t tris_cap, uint32_t info[5]);
 /* Scene geometry summary after nb_build_accel. */
 int nb_scene_info(nb_ctx *, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_bytes, int *bvh_depth);
 

@@ -75,6 +75,9 @@ def lib():
         L.nb_clear_meshes.argtypes = [vp]
         L.nb_build_accel.argtypes = [vp]
         L.nb_upload_scene.argtypes = [vp]
+        L.nb_set_accel_cache.argtypes = [vp, C.c_char_p]
+        L.nb_accel_cache_hit.argtypes = [vp]
+        L.nb_debug_bvh_cache.argtypes = [vp, vp, u32, i, C.c_int64, C.c_char_p, vp, u64, vp, u64, vp]
         L.nb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i)]
         L.nb_set_camera.argtypes = [vp, vp, vp, i, i, f, f]
         L.nb_set_filter.argtypes = [vp, vp, f]
@@ -96,6 +99,7 @@ def lib():
         L.nb_intersect_device.argtypes = [vp, vp, u64, vp, i, vp, sp]
         L.nb_intersect_full.argtypes = [vp, vp, u64, vp]
         L.nb_film_to_rgb.argtypes = [vp, vp, vp]
+        L.nb_last_film_to_srgb8.argtypes = [vp, vp]
         L.nb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         L.nb_debug_counters.argtypes = [vp, vp]
         L.nb_debug_build_bvh.argtypes = [vp, vp, u32, i, C.c_int64, vp, u64, vp, u64, vp]
@@ -128,6 +132,24 @@ def debug_build_bvh(V: np.ndarray, F: np.ndarray, max_leaf=3, bfs_nodes=2048):
     if rc:
         raise NoriError(f"nb_debug_build_bvh failed ({rc})")
     return nodes, tris, dict(nodes=int(info[0]), tris=int(info[1]), top_nodes=int(info[2]), depth=int(info[3]))
+
+
+def debug_bvh_cache(V: np.ndarray, F: np.ndarray, path: str, max_leaf=3, bfs_nodes=2048):
+    """nb_debug_bvh_cache (no GPU): the load-or-build-and-save step of nb_build_accel with nb_set_accel_cache.
+    Returns (nodes, tris, info) with info["hit"]."""
+    L = lib()
+    v4 = np.zeros((V.shape[0], 4), dtype=np.float32); v4[:, :3] = V
+    f4 = np.zeros((F.shape[0], 4), dtype=np.uint32); f4[:, :3] = F
+    info = np.zeros(5, dtype=np.uint32)
+    rc = L.nb_debug_bvh_cache(_p(v4), _p(f4), F.shape[0], max_leaf, bfs_nodes, os.fspath(path).encode(), None, 0, None, 0, _p(info))
+    if rc:
+        raise NoriError(f"nb_debug_bvh_cache failed ({rc})")
+    nodes = np.zeros((int(info[0]), 16), dtype=np.float32); tris = np.zeros((int(info[1]), 12), dtype=np.float32)
+    first_hit = int(info[4])
+    rc = L.nb_debug_bvh_cache(_p(v4), _p(f4), F.shape[0], max_leaf, bfs_nodes, os.fspath(path).encode(), _p(nodes), nodes.size, _p(tris), tris.size, _p(info))
+    if rc:
+        raise NoriError(f"nb_debug_bvh_cache failed ({rc})")
+    return nodes, tris, dict(nodes=int(info[0]), tris=int(info[1]), top_nodes=int(info[2]), depth=int(info[3]), hit=bool(first_hit))
 
 
 class Context:
@@ -230,6 +252,13 @@ class Context:
             lp = np.ascontiguousarray(scene.light_pos, dtype=np.float32)
             le = np.ascontiguousarray(scene.light_energy, dtype=np.float32)
             _check(L.nb_set_point_light(self.h, _p(lp), _p(le)))
+
+    def set_accel_cache(self, path):
+        _check(lib().nb_set_accel_cache(self.h, os.fspath(path).encode() if path else None))
+
+    @property
+    def accel_cache_hit(self) -> bool:
+        return bool(lib().nb_accel_cache_hit(self.h))
 
     def build_stats(self):
         sec, b = C.c_double(), C.c_int()
@@ -336,6 +365,12 @@ class Context:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         out = np.zeros((rays.shape[0], 16), dtype=np.float32)
         _check(lib().nb_intersect_full(self.h, _p(rays), rays.shape[0], _p(out)))
+        return out
+
+    def last_film_to_srgb8(self):
+        """nb_last_film_to_srgb8: the last nb_render's film, normalised + sRGB-tonemapped + quantised on the device: (H, W, 3) uint8."""
+        out = np.zeros((self.scene.camera.height, self.scene.camera.width, 3), dtype=np.uint8)
+        _check(lib().nb_last_film_to_srgb8(self.h, _p(out)))
         return out
 
     def film_to_rgb(self, film: np.ndarray):

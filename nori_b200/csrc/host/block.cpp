@@ -127,18 +127,31 @@ void Bitmap::saveEXR(const std::string &filename) const {
     }
 }
 
-/// sRGB 8-bit PNG with stored (uncompressed) deflate blocks (ref: src/bitmap.cpp:93-122 uses stb_image_write)
-void Bitmap::savePNG(const std::string &filename) const {
-    std::string path = filename + ".png";
+/// The 8-bit sRGB image of savePNG (ref: src/bitmap.cpp:93-122: toSRGB, x255, clamp), 3 bytes per pixel
+void Bitmap::toSRGB8(std::vector<uint8_t> &out) const {
     const int w = cols(), h = rows();
+    out.resize((size_t) w * h * 3);
+    for (size_t i = 0; i < (size_t) w * h; ++i) {
+        const float *p = &m_px[3 * i];
+        Color3f t = Color3f(p[0], p[1], p[2]).toSRGB();
+        for (int c = 0; c < 3; ++c) out[3 * i + c] = (uint8_t) std::min(255.f, std::max(0.f, 255.f * t.c[c]));   // clamp: ref src/bitmap.cpp:107-109
+    }
+}
+
+void Bitmap::savePNG(const std::string &filename) const {
+    std::vector<uint8_t> rgb8;
+    toSRGB8(rgb8);
+    savePNG8(filename, cols(), rows(), rgb8.data());
+}
+
+/// sRGB 8-bit PNG with stored (uncompressed) deflate blocks (ref: src/bitmap.cpp:93-122 uses stb_image_write).  rgb8 is
+/// already tonemapped: by toSRGB8 above, or on the device by nb_last_film_to_srgb8 (the same bytes).
+void Bitmap::savePNG8(const std::string &filename, int w, int h, const uint8_t *rgb8) {
+    std::string path = filename + ".png";
     std::string raw; raw.reserve((size_t) h * (1 + 3 * w));
     for (int y = 0; y < h; ++y) {
         raw.push_back('\0');
-        for (int x = 0; x < w; ++x) {
-            const float *p = &m_px[3 * ((size_t) y * w + x)];
-            Color3f t = Color3f(p[0], p[1], p[2]).toSRGB();
-            for (int c = 0; c < 3; ++c) raw.push_back((char) (uint8_t) std::min(255.f, std::max(0.f, 255.f * t.c[c])));   // clamp: ref src/bitmap.cpp:107-109
-        }
+        raw.append((const char *) rgb8 + (size_t) y * w * 3, (size_t) w * 3);
     }
     std::string z; z.push_back((char) 0x78); z.push_back((char) 0x01);
     uint32_t a = 1, b = 0;

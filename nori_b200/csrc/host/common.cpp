@@ -1,5 +1,6 @@
 // common.cpp -- string helpers, Matrix4f / Transform arithmetic, object + factory, property list.
 // (ref: src/common.cpp, src/object.cpp, src/proplist.cpp)
+#include <cstring>
 #include <algorithm>
 #include <iomanip>
 #include <sstream>
@@ -93,12 +94,46 @@ std::string memString(size_t size, bool precise) {                    // ref: sr
     return os.str();
 }
 
+// x^(1/2.4) as exp(log(x) / 2.4) with the single-precision Cephes polynomials the device code uses (nb_device.cuh det_logf /
+// det_expf; every multiply and add rounds separately on both sides), so that the host tonemap and film_to_srgb8_kernel
+// produce the SAME 8-bit image -- std::pow and the device pow differ in the last ulp, which flips a byte now and then.
+static float srgbLog(float xin) {
+    uint32_t b; std::memcpy(&b, &xin, 4);
+    int e = (int) ((b >> 23) & 0xff) - 126;
+    uint32_t mb = (b & 0x007fffffu) | 0x3f000000u;
+    float x; std::memcpy(&x, &mb, 4);
+    if (x < 0.70710678118654752440f) { e -= 1; x = x + x - 1.0f; } else { x = x - 1.0f; }
+    float z = x * x;
+    float y = ((((((((7.0376836292e-2f * x - 1.1514610310e-1f) * x + 1.1676998740e-1f) * x - 1.2420140846e-1f) * x
+              + 1.4249322787e-1f) * x - 1.6668057665e-1f) * x + 2.0000714765e-1f) * x - 2.4999993993e-1f) * x
+              + 3.3333331174e-1f) * x * z;
+    float fe = (float) e;
+    y = y + (-2.12194440e-4f * fe);
+    y = y + (-0.5f * z);
+    z = x + y;
+    z = z + 0.693359375f * fe;
+    return z;
+}
+static float srgbExp(float x) {
+    if (x < -87.0f) return 0.0f;
+    if (x > 88.0f) x = 88.0f;
+    float z = std::floor(1.44269504088896341f * x + 0.5f);
+    x = x - z * 0.693359375f;
+    x = x - z * -2.12194440e-4f;
+    int n = (int) z;
+    z = x * x;
+    z = (((((1.9875691500e-4f * x + 1.3981999507e-3f) * x + 8.3334519073e-3f) * x + 4.1665795894e-2f) * x
+        + 1.6666665459e-1f) * x + 5.0000001201e-1f) * z + x + 1.0f;
+    uint32_t sb = (uint32_t) (n + 127) << 23; float sc; std::memcpy(&sc, &sb, 4);
+    return z * sc;
+}
+
 Color3f Color3f::toSRGB() const {                                     // ref: src/common.cpp:166-180
     Color3f result;
     for (int i = 0; i < 3; ++i) {
         float value = c[i];
         if (value <= 0.0031308f) result.c[i] = 12.92f * value;
-        else result.c[i] = (1.0f + 0.055f) * std::pow(value, 1.0f / 2.4f) - 0.055f;
+        else result.c[i] = (1.0f + 0.055f) * srgbExp(srgbLog(value) * (1.0f / 2.4f)) - 0.055f;
     }
     return result;
 }

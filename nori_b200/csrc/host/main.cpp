@@ -1,6 +1,7 @@
 // main.cpp -- `nori <scene.xml>` command line (ref: src/main.cpp:150-246).  --no-gui / --threads are accepted for
 // compatibility and ignored (there is no GUI and no TBB on this path); --device N selects the GPU, --gpus N
-// renders on N devices (tiles sharded tile_id % N, finished ImageBlocks gathered over NCCL, merged on the first device).
+// renders on N devices (tiles sharded tile_id % N, finished ImageBlocks gathered over NCCL, merged on the first device),
+// --cache keeps the built BVH in <scene>.nbbvh and reloads it when the geometry is unchanged.
 #include <cstring>
 #include "nori/parser.h"
 #include "nori/render.h"
@@ -9,7 +10,7 @@ using namespace nori;
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N] [--gpus N] [--lbvh]" << endl;
+        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N] [--gpus N] [--lbvh] [--cache]" << endl;
         return -1;
     }
     std::string sceneName;
@@ -22,6 +23,8 @@ int main(int argc, char **argv) {
         } else if (token == "--no-gui") {
         } else if (token == "--lbvh") {
             opt.deviceBuilder = true;   // GPU-built hierarchy (fast build, slightly slower render)
+        } else if (token == "--cache") {
+            opt.accelCache = "?";       // resolved below: <scene>.nbbvh next to the scene file
         } else if (token == "--gpus") {
             if (i + 1 >= argc || atoi(argv[i + 1]) < 1) { cerr << "\"--gpus\" expects a positive integer following it." << endl; return -1; }
             opt.gpus = atoi(argv[++i]);   // devices device .. device+N-1 render tile shards; blocks gathered over NCCL
@@ -36,6 +39,7 @@ int main(int argc, char **argv) {
         if (endsWith(toLower(sceneName), ".xml")) {
             std::unique_ptr<NoriObject> root(loadFromXML(sceneName));
             /* When the XML root object is a scene, start rendering it (ref: src/main.cpp:236-238) */
+            if (opt.accelCache == "?") opt.accelCache = sceneName.substr(0, sceneName.size() - 4) + ".nbbvh";
             if (root->getClassType() == NoriObject::EScene) {
                 cout << endl << "Configuration: " << root->toString() << endl << endl;
                 render(static_cast<Scene *>(root.get()), sceneName, opt);

@@ -62,6 +62,8 @@ public:
     const float *data() const { return m_px.data(); }
     void saveEXR(const std::string &filename) const;            // uncompressed fp32 scanline OpenEXR ("<name>.exr")
     void savePNG(const std::string &filename) const;            // sRGB 8-bit ("<name>.png"), ref: src/bitmap.cpp:93-122
+    void toSRGB8(std::vector<uint8_t> &out) const;              // the tonemapped bytes savePNG writes (host loop)
+    static void savePNG8(const std::string &filename, int w, int h, const uint8_t *rgb8);   // PNG of already tonemapped bytes
 private:
     Vector2i m_size;
     std::vector<float> m_px;

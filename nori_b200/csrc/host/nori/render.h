@@ -15,6 +15,7 @@ struct RenderOptions {
     int tileRank = 0, tileRanks = 1;   // tile shard (multi-GPU: one process per GPU)
     bool quiet = false;
     bool deviceBuilder = false;        // build the hierarchy on the GPU (LBVH) instead of the host SAH builder
+    std::string accelCache;            // file caching the built hierarchy (nb_set_accel_cache); empty = build every time
 };
 
 /// Builds the GPU context for a scene: meshes + plugin descriptors (from the factory's creation records), BVH,
@@ -25,7 +26,9 @@ nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const Rend
 void describeBSDF(const BSDF *bsdf, nb_bsdf_desc *out);
 
 /// Replaces the body of render(): fills `result` (the full-image ImageBlock) through nb_render.
-void renderScene(Scene *scene, ImageBlock &result, const RenderOptions &opt, nb_stats *stats = nullptr);
+/// srgb8 (optional): the W x H x 3 tonemapped 8-bit image, produced on the device from the film it still holds
+/// (nb_last_film_to_srgb8) -- what the PNG writer consumes.
+void renderScene(Scene *scene, ImageBlock &result, const RenderOptions &opt, nb_stats *stats = nullptr, std::vector<uint8_t> *srgb8 = nullptr);
 
 /// Full driver: render + toBitmap + EXR/PNG next to the scene file (ref: src/main.cpp:127-147)
 void render(Scene *scene, const std::string &filename, const RenderOptions &opt);

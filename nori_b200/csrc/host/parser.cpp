@@ -187,9 +187,15 @@ NoriObject *parseTag(ParseContext &cx, XmlNode &node, PropertyList &list, int pa
 
     PropertyList propList;
     std::vector<NoriObject *> children;
-    for (auto &ch : node.children) {
-        NoriObject *child = parseTag(cx, *ch, propList, tag);
-        if (child) children.push_back(child);
+    size_t adopted = 0;                 // children[0 .. adopted) belong to `result` (its destructor deletes them)
+    try {
+        for (auto &ch : node.children) {
+            NoriObject *child = parseTag(cx, *ch, propList, tag);
+            if (child) children.push_back(child);
+        }
+    } catch (...) {                     // a later sibling failed: the ones already built have no owner yet
+        for (NoriObject *ch : children) delete ch;
+        throw;
     }
 
     NoriObject *result = nullptr;
@@ -201,7 +207,7 @@ NoriObject *parseTag(ParseContext &cx, XmlNode &node, PropertyList &list, int pa
                 throw NoriException("Unexpectedly constructed an object of type <%s> (expected type <%s>): %s",
                                     NoriObject::classTypeName(result->getClassType()),
                                     NoriObject::classTypeName((NoriObject::EClassType) tag), result->toString());
-            for (auto ch : children) { result->addChild(ch); ch->setParent(result); }
+            for (auto ch : children) { result->addChild(ch); ++adopted; ch->setParent(result); }
             result->activate();
         } else {
             auto A = [&](const char *k) -> const std::string & { return *node.attr(k); };
@@ -269,7 +275,8 @@ NoriObject *parseTag(ParseContext &cx, XmlNode &node, PropertyList &list, int pa
             }
         }
     } catch (const NoriException &e) {
-        for (auto ch : children) (void) ch;
+        for (size_t i = adopted; i < children.size(); ++i) delete children[i];   // not (yet) owned by anybody
+        delete result;                                                           // takes the adopted children with it
         throw NoriException("Error while parsing \"%s\": %s (at %s)", cx.filename, std::string(e.what()), cx.reader->where(node.offset));
     }
     return result;
@@ -277,7 +284,9 @@ NoriObject *parseTag(ParseContext &cx, XmlNode &node, PropertyList &list, int pa
 
 }  // namespace
 
-static std::string g_sceneDir;
+// Directory of the scene file being loaded.  Per thread, and restored when loadFromXML returns, so that concurrent or
+// nested loads resolve their OBJ paths against their own scene file.
+static thread_local std::string g_sceneDir;
 const std::string &sceneDirectory() { return g_sceneDir; }
 
 std::string resolvePath(const std::string &name) {   // stands in for filesystem::resolver (ref: src/main.cpp:195-197, src/obj.cpp:24-25)
@@ -305,7 +314,11 @@ NoriObject *loadFromXML(const std::string &filename) {
     if (is.fail()) throw NoriException("Error while parsing \"%s\": unable to open the file", filename);
     std::stringstream ss; ss << is.rdbuf();
     size_t slash = filename.find_last_of('/');
-    g_sceneDir = slash == std::string::npos ? std::string(".") : filename.substr(0, slash);
+    struct DirScope {
+        std::string saved;
+        explicit DirScope(std::string dir) : saved(g_sceneDir) { g_sceneDir = std::move(dir); }
+        ~DirScope() { g_sceneDir = saved; }
+    } scope(slash == std::string::npos ? std::string(".") : filename.substr(0, slash));
     return loadFromXMLString(ss.str(), filename);
 }
 

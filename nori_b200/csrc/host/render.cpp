@@ -85,6 +85,7 @@ nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const Rend
     }
     try {
         if (opt.deviceBuilder && nb_set_option(ctx, "builder", 1)) throwLast("nb_set_option");
+        if (!opt.accelCache.empty() && nb_set_accel_cache(ctx, opt.accelCache.c_str())) throwLast("nb_set_accel_cache");
         for (const Mesh *mesh : scene->getMeshes()) {   // Scene::addChild(mesh) -> Accel::addMesh (ref: src/scene.cpp:48-53)
             nb_bsdf_desc b = describeBSDF(mesh->getBSDF());
             nb_emitter_desc e;
@@ -121,12 +122,16 @@ nb_ctx *createDeviceScene(const Scene *scene, const ImageBlock &film, const Rend
     return ctx;
 }
 
-void renderScene(Scene *scene, ImageBlock &result, const RenderOptions &opt, nb_stats *stats) {
+void renderScene(Scene *scene, ImageBlock &result, const RenderOptions &opt, nb_stats *stats, std::vector<uint8_t> *srgb8) {
     scene->getIntegrator()->preprocess(scene);                    // ref: src/main.cpp:61
     nb_ctx *ctx = createDeviceScene(scene, result, opt);
     nb_stats st; std::memset(&st, 0, sizeof st);
     result.clear();
     int rc = nb_render(ctx, result.data(), &st);                  // replaces ref: src/main.cpp:64-119
+    if (!rc && srgb8) {                                           // tonemap + 8-bit pack on the device (ref: src/common.cpp:166-180, src/bitmap.cpp:100-110)
+        srgb8->resize((size_t) result.getSize().x() * result.getSize().y() * 3);
+        rc = nb_last_film_to_srgb8(ctx, srgb8->data());
+    }
     std::string err = rc ? nb_last_error() : "";
     nb_destroy(ctx);
     if (rc) throw NoriException("nb_render: %s", err);
@@ -139,7 +144,8 @@ void render(Scene *scene, const std::string &filename, const RenderOptions &opt)
     if (!opt.quiet) { cout << "Rendering .. "; cout.flush(); }
     nb_stats st;
     auto t0 = std::chrono::steady_clock::now();
-    renderScene(scene, result, opt, &st);
+    std::vector<uint8_t> srgb8;
+    renderScene(scene, result, opt, &st, &srgb8);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (!opt.quiet)
         cout << "done. (took " << timeString(ms) << " incl. upload + BVH build; render kernel " << timeString(st.kernel_ms, true) << ", "
@@ -149,7 +155,7 @@ void render(Scene *scene, const std::string &filename, const RenderOptions &opt)
     size_t lastdot = outputName.find_last_of(".");
     if (lastdot != std::string::npos) outputName.erase(lastdot, std::string::npos);
     bitmap->saveEXR(outputName);
-    bitmap->savePNG(outputName);
+    Bitmap::savePNG8(outputName, bitmap->cols(), bitmap->rows(), srgb8.data());   // bytes from film_to_srgb8_kernel
 }
 
 NORI_NAMESPACE_END
@@ -214,13 +220,22 @@ int nori_host_mesh(void *scene_, int i, uint32_t *nv, uint32_t *nf, const float 
 }
 
 /// Renders through the C-ABI (GPU required).  film: (H+2b) x (W+2b) x 4 floats.
-int nori_host_render_gpus(void *scene_, int device, int gpus, float *film, nb_stats *stats) {
+int nori_host_render_gpus(void *scene_, int device, int gpus, const char *accel_cache, float *film, uint8_t *srgb8_device, uint8_t *srgb8_host,
+                          nb_stats *stats) {
     try {
         nori::Scene *scene = static_cast<nori::Scene *>(scene_);
         nori::ImageBlock blk(scene->getCamera()->getOutputSize(), scene->getCamera()->getReconstructionFilter());
         nori::RenderOptions opt; opt.device = device; opt.gpus = gpus; opt.quiet = true;
-        nori::renderScene(scene, blk, opt, stats);
+        if (accel_cache) opt.accelCache = accel_cache;
+        std::vector<uint8_t> dev8;
+        nori::renderScene(scene, blk, opt, stats, srgb8_device ? &dev8 : nullptr);
         std::memcpy(film, blk.data(), sizeof(float) * 4 * (size_t) blk.rows() * blk.cols());
+        if (srgb8_device) std::memcpy(srgb8_device, dev8.data(), dev8.size());
+        if (srgb8_host) {      // the host loop (Bitmap::toSRGB8) on the same film, for the byte-equality test
+            std::unique_ptr<nori::Bitmap> bmp(blk.toBitmap());
+            std::vector<uint8_t> h8; bmp->toSRGB8(h8);
+            std::memcpy(srgb8_host, h8.data(), h8.size());
+        }
         return 0;
     } catch (const std::exception &e) { g_host_err = e.what(); return 1; }
 }

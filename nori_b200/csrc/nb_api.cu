@@ -350,6 +350,11 @@ int build_lbvh_device(nb_ctx *c, size_t nf, float pad, const float clo[3], const
     LCK(cub::DeviceRadixSort::SortKeys(L.cub_tmp, L.cub_bytes, L.keys, L.keys_sorted, n, 0, 62, s));
     nb::lbvh_leaf_boxes_kernel<<<G, B, 0, s>>>(c->verts.d, c->faces.d, L.keys_sorted, (unsigned) n, pad, L.leaf_lo, L.leaf_hi);
     nb::lbvh_hierarchy_kernel<<<G, B, 0, s>>>(L.keys_sorted, n, L.children, L.parent, L.range);
+    int *depth_d = reinterpret_cast<int *>(c->counters);          // scratch: the counters are cleared by every render
+    LCK(cudaMemsetAsync(depth_d, 0, sizeof(int), s));
+    nb::lbvh_depth_kernel<<<G, B, 0, s>>>(n, L.parent, depth_d);
+    int tree_depth = 0;
+    LCK(cudaMemcpyAsync(&tree_depth, depth_d, sizeof(int), cudaMemcpyDeviceToHost, s));
     LCK(cudaMemsetAsync(L.arrive, 0, sizeof(unsigned) * n, s));
     nb::lbvh_fit_kernel<<<G, B, 0, s>>>(n, L.children, L.parent, L.leaf_lo, L.leaf_hi, L.node_lo, L.node_hi, L.arrive);
     nb::lbvh_mark_kernel<<<G, B, 0, s>>>(n, L.range, (int) std::max<int64_t>(1, std::min<int64_t>(8, c->opt_max_leaf)), L.emit);
@@ -360,6 +365,7 @@ int build_lbvh_device(nb_ctx *c, size_t nf, float pad, const float clo[3], const
     LCK(cudaStreamSynchronize(s));
     const unsigned nnodes = last_idx + last_emit;
     if (nnodes == 0) { cleanup(); return fail("LBVH: empty hierarchy"); }
+    if (tree_depth >= nb::kStack - 1) { cleanup(); return fail("LBVH too deep (%d levels; the traversal stack holds %d)", tree_depth, nb::kStack); }
     LCK(c->nodes.alloc((size_t) nnodes * 4)); LCK(c->tris.alloc((size_t) n * 3));
     nb::lbvh_emit_nodes_kernel<<<G, B, 0, s>>>(n, L.children, L.range, L.emit, L.emit_index, L.leaf_lo, L.leaf_hi, L.node_lo, L.node_hi, c->nodes.d);
     nb::lbvh_emit_tris_kernel<<<G, B, 0, s>>>(c->verts.d, c->faces.d, L.keys_sorted, (unsigned) n, c->tris.d);
@@ -369,7 +375,7 @@ int build_lbvh_device(nb_ctx *c, size_t nf, float pad, const float clo[3], const
     LCK(cudaStreamSynchronize(s));
 #undef LCK
     cleanup();
-    c->n_nodes = nnodes; c->top_nodes = 0; c->bvh_depth = 0;
+    c->n_nodes = nnodes; c->top_nodes = 0; c->bvh_depth = tree_depth;
     return rc;
 }
 
@@ -569,7 +575,15 @@ static int build_accel_local(nb_ctx *c) {
     nb::BvhInput in; in.verts = reinterpret_cast<const float *>(c->verts.h); in.faces = reinterpret_cast<const uint32_t *>(c->faces.h);
     in.nprims = (uint32_t) nf;
     nb::BvhOutput out;
-    nb::build_bvh(in, out, (int) c->opt_max_leaf, c->opt_bfs_nodes < 0 ? nb::kSiblingPairs : (uint32_t) c->opt_bfs_nodes, 0);
+    const uint32_t bfs = c->opt_bfs_nodes < 0 ? nb::kSiblingPairs : (uint32_t) c->opt_bfs_nodes;
+    // on-disk hierarchy cache (nb_set_accel_cache): keyed on every vertex / index the builder reads + the build parameters
+    uint64_t key = 0; bool hit = false;
+    if (!c->accel_cache.empty()) { key = nb::bvh_cache_key(in, (int) c->opt_max_leaf, bfs); hit = nb::bvh_cache_load(c->accel_cache.c_str(), key, out); }
+    if (!hit) {
+        nb::build_bvh(in, out, (int) c->opt_max_leaf, bfs, 0);
+        if (!c->accel_cache.empty()) nb::bvh_cache_save(c->accel_cache.c_str(), key, out);
+    }
+    c->accel_cache_hit = hit;
     c->n_nodes = out.nnodes; c->top_nodes = out.top_nodes; c->bvh_depth = out.depth;
     c->build_seconds = out.build_seconds; c->builder_used = 0;
     if (out.depth >= nb::kStack) return fail("BVH too deep (%d)", out.depth);
@@ -579,6 +593,14 @@ static int build_accel_local(nb_ctx *c) {
     c->built = true;
     return upload_local(c);
 }
+
+int nb_set_accel_cache(nb_ctx *c, const char *path) {
+    if (!c) return fail("null context");
+    c->accel_cache = path ? path : "";
+    return 0;
+}
+
+int nb_accel_cache_hit(nb_ctx *c) { return (c && c->built && c->accel_cache_hit) ? 1 : 0; }
 
 int nb_build_stats(nb_ctx *c, double *seconds, int *builder) {
     if (!c) return fail("null context");
@@ -593,7 +615,7 @@ int nb_set_camera(nb_ctx *c, const float s2c[16], const float c2w[16], int width
     if (!s2c || !c2w) return fail("nb_set_camera: null matrix");
     if (width <= 0 || height <= 0 || width > 32767 || height > 32767) return fail("invalid output size %dx%d", width, height);
     memcpy(c->s2c, s2c, sizeof c->s2c); memcpy(c->c2w, c2w, sizeof c->c2w);
-    c->W = width; c->H = height; c->nearClip = nearClip; c->farClip = farClip; c->have_camera = true;
+    c->W = width; c->H = height; c->nearClip = nearClip; c->farClip = farClip; c->have_camera = true; c->film_valid = false;
     for (nb_ctx *f : c->followers) if (nb_set_camera(f, s2c, c2w, width, height, nearClip, farClip)) return 1;
     return 0;
 }
@@ -605,7 +627,7 @@ int nb_set_filter(nb_ctx *c, const float table[NB_FILTER_RESOLUTION + 1], float 
     int border = (int) std::ceil(radius - 0.5f);     // ref: src/block.cpp:20
     if (border > 8) return fail("filter radius %f too large", radius);
     memcpy(c->ftable, table, sizeof c->ftable);
-    c->fradius = radius; c->border = border;
+    c->fradius = radius; c->border = border; c->film_valid = false;
     for (nb_ctx *f : c->followers) if (nb_set_filter(f, table, radius)) return 1;
     return 0;
 }
@@ -734,6 +756,7 @@ int nb_render(nb_ctx *c, float *film_host, nb_stats *st) {
         // statistics after the film copy is queued: one synchronisation for the whole frame
         if (nbm::render_group_stats(c, s, st)) return 1;
         st->d2h_bytes = c->comm_rank == 0 ? sizeof(float4) * film_elems : 0; st->h2d_bytes = sizeof(nb::RenderParams);
+        c->film_valid = c->comm_rank == 0;
         return 0;
     }
     int n_tiles = 0;
@@ -743,6 +766,7 @@ int nb_render(nb_ctx *c, float *film_host, nb_stats *st) {
     CK(cudaMemcpyAsync(film_host, c->film, sizeof(float4) * film_elems, cudaMemcpyDeviceToHost, s));
     if (finish_stats(c, s, st, n_tiles > 0 ? 1 : 0)) return 1;
     if (st) { st->d2h_bytes = sizeof(float4) * film_elems; st->h2d_bytes = sizeof(nb::RenderParams); }
+    c->film_valid = true;
     return 0;
 }
 
@@ -885,13 +909,15 @@ int nb_intersect_full(nb_ctx *c, const nb_ray *rays, uint64_t n, float *out16) {
     CK(cudaMalloc(&dr, sizeof(nb_ray) * n));
     if (cudaMalloc(&df, sizeof(float) * 16 * n) != cudaSuccess) { cudaFree(dr); return fail("cudaMalloc failed"); }
     int rc = 0;
-    if (cudaMemcpy(dr, rays, sizeof(nb_ray) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("H2D copy failed");
+    // copies and kernel on the SAME (non-blocking) stream: a pageable cudaMemcpy on the legacy stream does not order with it
+    if (cudaMemcpyAsync(dr, rays, sizeof(nb_ray) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = fail("H2D copy failed");
     if (!rc) {
         int grid = (int) std::min<uint64_t>((n + 127) / 128, (uint64_t) c->sm_count * 16);
         nb::intersect_kernel<false><<<grid, 128, 0, c->stream>>>(sc, reinterpret_cast<const float4 *>(dr), n, nullptr, 0, df, nullptr);
-        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("intersect kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (cudaGetLastError() != cudaSuccess) rc = fail("intersect kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    if (!rc && cudaMemcpy(out16, df, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
+    if (!rc && cudaMemcpyAsync(out16, df, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = fail("D2H copy failed");
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) rc = fail("intersect kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(dr); cudaFree(df);
     return rc;
 }
@@ -905,14 +931,34 @@ int nb_film_to_rgb(nb_ctx *c, const float *film_host, float *rgb_host) {
     CK(cudaMalloc(&df, sizeof(float4) * film_elems));
     if (cudaMalloc(&dr, sizeof(float) * 3 * c->W * c->H) != cudaSuccess) { cudaFree(df); return fail("cudaMalloc failed"); }
     int rc = 0;
-    if (cudaMemcpy(df, film_host, sizeof(float4) * film_elems, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("H2D copy failed");
+    if (cudaMemcpyAsync(df, film_host, sizeof(float4) * film_elems, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = fail("H2D copy failed");
     if (!rc) {
         nb::film_to_rgb_kernel<<<(c->W * c->H + 255) / 256, 256, 0, c->stream>>>(df, c->W, c->H, c->border, dr);
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("film_to_rgb kernel failed");
+        if (cudaGetLastError() != cudaSuccess) rc = fail("film_to_rgb kernel failed");
     }
-    if (!rc && cudaMemcpy(rgb_host, dr, sizeof(float) * 3 * c->W * c->H, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
+    if (!rc && cudaMemcpyAsync(rgb_host, dr, sizeof(float) * 3 * c->W * c->H, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = fail("D2H copy failed");
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) rc = fail("film_to_rgb kernel failed");
     cudaFree(df); cudaFree(dr);
     return rc;
+}
+
+int nb_last_film_to_srgb8(nb_ctx *c, uint8_t *rgb8_host) {
+    if (!c || !rgb8_host) return fail("null argument");
+    if (c->leader) return fail("nb_last_film_to_srgb8: call it on the group's leader context");
+    if (ensure_device(c)) return 1;
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
+    if (!c->film || !c->film_valid || c->film_cap < film_elems) return fail("nb_last_film_to_srgb8: no film on the device (call nb_render first)");
+    const size_t n = (size_t) c->W * c->H * 3;
+    unsigned char *d8 = nullptr;
+    CK(cudaMalloc(&d8, n));
+    nb::film_to_srgb8_kernel<<<(c->W * c->H + 255) / 256, 256, 0, c->stream>>>(c->film, c->W, c->H, c->border, d8);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb8_host, d8, n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d8);
+    if (e != cudaSuccess) return fail("film_to_srgb8 kernel failed: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
@@ -922,7 +968,14 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     else if (k == "smem_nodes") c->opt_smem_nodes = value;
     else if (k == "chunk") c->opt_chunk = value;
     else if (k == "count") c->opt_count = value;
-    else if (k == "tail") { if (value < 0 || value > 31) return fail("tail must be in [0, 31]"); c->opt_tail = value; }
+    else if (k == "tail") {
+#if NB_TAIL_CUT
+        if (value < 0 || value > 31) return fail("tail must be in [0, 31]");
+        c->opt_tail = value;
+#else
+        if (value != 0) return fail("option \"tail\" needs a library built with -DNB_TAIL_CUT=1 (this build walks every ray to completion)");
+#endif
+    }
     else if (k == "engine") { if (value != 0 && value != 1) return fail("engine must be 0 (fused) or 1 (deferred occlusion)"); c->opt_engine = value; }
     else if (k == "occ_mb") { if (value < 1 || value > 65536) return fail("occ_mb must be in [1, 65536]"); c->opt_occ_mb = value; }
     else if (k == "occ_tail") { if (value < 0 || value > 31) return fail("occ_tail must be in [0, 31]"); c->opt_occ_tail = value; }

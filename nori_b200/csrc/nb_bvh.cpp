@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <string>
 #include <thread>
 
 namespace nb {
@@ -358,7 +359,95 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ------------------------------------------------------------------ on-disk cache (see nb_bvh.h)
+namespace {
+struct CacheHeader {
+    char magic[8];              // "NBBVH002": layout version of nodes / tris
+    uint64_t key;
+    uint32_t nnodes, ntris, top_nodes; int32_t depth;
+    float scene_lo[3], scene_hi[3];
+    uint64_t payload_hash;      // FNV-1a of the node and triangle bytes: a truncated or damaged file misses
+};
+inline uint64_t fnv1a(const void *data, size_t n, uint64_t h) {
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    // 8 bytes per step (the arrays are 4-byte words; a tail of < 8 bytes is folded bytewise)
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, p + i, 8); h = (h ^ w) * 0x100000001b3ull; }
+    for (; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+}  // namespace
+
+uint64_t bvh_cache_key(const BvhInput &in, int max_leaf, uint32_t bfs_nodes) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    const uint32_t params[4] = { in.nprims, (uint32_t) max_leaf, bfs_nodes, 2u /* layout version */ };
+    h = fnv1a(params, sizeof params, h);
+    uint32_t max_v = 0;
+    for (uint32_t i = 0; i < in.nprims; ++i) for (int k = 0; k < 3; ++k) max_v = std::max(max_v, in.faces[4 * (size_t) i + k]);
+    h = fnv1a(in.faces, sizeof(uint32_t) * 4 * (size_t) in.nprims, h);
+    if (in.nprims) h = fnv1a(in.verts, sizeof(float) * 4 * ((size_t) max_v + 1), h);
+    return h;
+}
+
+bool bvh_cache_load(const char *path, uint64_t key, BvhOutput &out) {
+    FILE *f = path ? fopen(path, "rb") : nullptr;
+    if (!f) return false;
+    CacheHeader hd;
+    bool ok = fread(&hd, sizeof hd, 1, f) == 1 && std::memcmp(hd.magic, "NBBVH002", 8) == 0 && hd.key == key;
+    if (ok) {
+        out.nodes.resize((size_t) hd.nnodes * 16); out.tris.resize((size_t) hd.ntris * 12);
+        ok = fread(out.nodes.data(), sizeof(float), out.nodes.size(), f) == out.nodes.size() &&
+             fread(out.tris.data(), sizeof(float), out.tris.size(), f) == out.tris.size();
+        if (ok) {
+            uint64_t h = fnv1a(out.nodes.data(), out.nodes.size() * sizeof(float), 0xcbf29ce484222325ull);
+            h = fnv1a(out.tris.data(), out.tris.size() * sizeof(float), h);
+            ok = h == hd.payload_hash;
+        }
+    }
+    fclose(f);
+    if (!ok) { out.nodes.clear(); out.tris.clear(); return false; }
+    out.nnodes = hd.nnodes; out.top_nodes = hd.top_nodes; out.depth = hd.depth; out.build_seconds = 0;
+    for (int a = 0; a < 3; ++a) { out.scene_lo[a] = hd.scene_lo[a]; out.scene_hi[a] = hd.scene_hi[a]; }
+    return true;
+}
+
+bool bvh_cache_save(const char *path, uint64_t key, const BvhOutput &out) {
+    if (!path || !*path) return false;
+    const std::string tmp = std::string(path) + ".tmp";     // written aside and renamed: readers never see half a file
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    CacheHeader hd; std::memset(&hd, 0, sizeof hd);
+    std::memcpy(hd.magic, "NBBVH002", 8);
+    hd.key = key; hd.nnodes = out.nnodes; hd.ntris = (uint32_t) (out.tris.size() / 12); hd.top_nodes = out.top_nodes; hd.depth = out.depth;
+    for (int a = 0; a < 3; ++a) { hd.scene_lo[a] = out.scene_lo[a]; hd.scene_hi[a] = out.scene_hi[a]; }
+    hd.payload_hash = fnv1a(out.nodes.data(), out.nodes.size() * sizeof(float), 0xcbf29ce484222325ull);
+    hd.payload_hash = fnv1a(out.tris.data(), out.tris.size() * sizeof(float), hd.payload_hash);
+    bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(out.nodes.data(), sizeof(float), out.nodes.size(), f) == out.nodes.size() &&
+              fwrite(out.tris.data(), sizeof(float), out.tris.size(), f) == out.tris.size();
+    ok = fclose(f) == 0 && ok;
+    if (ok) ok = std::rename(tmp.c_str(), path) == 0;
+    if (!ok) std::remove(tmp.c_str());
+    return ok;
+}
+
 }  // namespace nb
+
+// Host-only diagnostic of the hierarchy cache (no context, no GPU; declared in include/nori_b200.h): what nb_build_accel does
+// with nb_set_accel_cache -- key, load or build + save.  info = { nodes, leaf triangles, top nodes, depth, cache hit (0/1) }.
+extern "C" int nb_debug_bvh_cache(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes,
+                                  const char *path, float *nodes_out, uint64_t nodes_cap, float *tris_out, uint64_t tris_cap, uint32_t info[5]) {
+    if ((nprims && (!verts4 || !faces4)) || !info || !path || max_leaf < 1 || max_leaf > 8) return 1;
+    nb::BvhInput in; in.verts = verts4; in.faces = faces4; in.nprims = nprims;
+    const uint32_t bfs = bfs_nodes < 0 ? nb::kSiblingPairs : (uint32_t) bfs_nodes;
+    const uint64_t key = nb::bvh_cache_key(in, max_leaf, bfs);
+    nb::BvhOutput out;
+    const bool hit = nb::bvh_cache_load(path, key, out);
+    if (!hit) { nb::build_bvh(in, out, max_leaf, bfs, 0); nb::bvh_cache_save(path, key, out); }
+    info[0] = out.nnodes; info[1] = (uint32_t) (out.tris.size() / 12); info[2] = out.top_nodes; info[3] = (uint32_t) out.depth; info[4] = hit ? 1u : 0u;
+    if (nodes_out) { if (nodes_cap < out.nodes.size()) return 2; std::memcpy(nodes_out, out.nodes.data(), out.nodes.size() * sizeof(float)); }
+    if (tris_out) { if (tris_cap < out.tris.size()) return 2; if (!out.tris.empty()) std::memcpy(tris_out, out.tris.data(), out.tris.size() * sizeof(float)); }
+    return 0;
+}
 
 // Host-only diagnostic entry (declared in include/nori_b200.h): runs the SAH builder on caller-provided arrays and
 // returns the device layout, so that the hierarchy can be checked without a GPU (tests/test_bvh_cpu.py).

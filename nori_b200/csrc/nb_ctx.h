@@ -61,7 +61,7 @@ struct nb_ctx {
     int tile_rank = 0, tile_nranks = 1;
     // work buffers
     float4 *blocks = nullptr; size_t blocks_cap = 0;
-    float4 *film = nullptr; size_t film_cap = 0;
+    float4 *film = nullptr; size_t film_cap = 0; bool film_valid = false;   // film_valid: holds the last nb_render's film
     unsigned long long *counters = nullptr;          // 8 x u64 device
     unsigned long long *counters_h = nullptr;        // pinned
     // options
@@ -69,6 +69,7 @@ struct nb_ctx {
             opt_bfs_nodes = 2048, opt_builder = 0, opt_tail = 0, opt_engine = 0, opt_occ_mb = 1024, opt_occ_tail = 20;
     float4 *occ_queue = nullptr; size_t occ_cap = 0;   // deferred-occlusion engine: ray queue (rays)
     int builder_used = 0;   // 0 host SAH, 1 device LBVH
+    std::string accel_cache; bool accel_cache_hit = false;   // on-disk hierarchy cache (nb_set_accel_cache)
     // ---- multi-GPU (nb_multi.inl)
     std::vector<nb_ctx *> followers;   // nb_create_multi: the contexts on the other devices (owned by this leader)
     nb_ctx *leader = nullptr;          // set on followers

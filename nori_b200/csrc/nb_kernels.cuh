@@ -1060,4 +1060,22 @@ __global__ void film_to_rgb_kernel(const float4 *film, int W, int H, int border,
     rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
 }
 
+// ImageBlock::toBitmap + Color3f::toSRGB + the 8-bit quantisation of Bitmap::savePNG in one pass over the film
+// (ref: src/block.cpp:45-51, src/common.cpp:166-180, src/bitmap.cpp:100-110).  x^(1/2.4) = exp(log(x) / 2.4) through the
+// deterministic polynomials shared with the host (csrc/host/common.cpp), so the bytes equal the host loop's.
+__global__ void film_to_srgb8_kernel(const float4 *film, int W, int H, int border, unsigned char *rgb8) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    const int y = i / W, x = i % W;
+    const float4 p = film[(size_t) (y + border) * (W + 2 * border) + (x + border)];
+    float c[3] = { 0.f, 0.f, 0.f };
+    if (p.w != 0.f) { c[0] = p.x / p.w; c[1] = p.y / p.w; c[2] = p.z / p.w; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float v = c[k];
+        const float t = v <= 0.0031308f ? 12.92f * v : (1.0f + 0.055f) * det_expf(det_logf(v) * (1.0f / 2.4f)) - 0.055f;
+        rgb8[3 * (size_t) i + k] = (unsigned char) fminf(255.f, fmaxf(0.f, 255.f * t));
+    }
+}
+
 }  // namespace nb

@@ -112,6 +112,17 @@ __global__ void lbvh_fit_kernel(int n, const int2 *children, const int *parent, 
     }
 }
 
+// Depth of the radix tree: every leaf climbs to the root and the longest climb is kept.  The 62-bit keys bound it by 62
+// (coincident centroids separate only in the index bits), close to the per-lane traversal stack (kStack = 64), so the
+// build checks it instead of trusting the bound.
+__global__ void lbvh_depth_kernel(int n, const int *parent, int *max_depth) {
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    int d = 1;
+    for (int node = parent[(n - 1) + leaf]; node >= 0; node = parent[node]) ++d;
+    atomicMax(max_depth, d);
+}
+
 // An internal node stays an inner node of the output iff it covers more than max_leaf triangles.
 __global__ void lbvh_mark_kernel(int n, const int2 *range, int max_leaf, unsigned *emit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

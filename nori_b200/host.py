@@ -30,7 +30,7 @@ def lib():
         L.nori_host_mesh.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(vp),
                                      C.POINTER(vp), C.POINTER(vp), C.POINTER(abi.BsdfDesc), C.POINTER(abi.EmitterDesc)]
         L.nori_host_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(abi.Stats)]
-        L.nori_host_render_gpus.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(abi.Stats)]
+        L.nori_host_render_gpus.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, vp, vp, vp, C.POINTER(abi.Stats)]
         L.nori_host_is_registered.argtypes = [C.c_char_p]
         L.nori_host_block_order.argtypes = [C.c_int, C.c_int, vp]
         _lib = L
@@ -99,19 +99,25 @@ class HostScene:
                     bsdf=dict(type=b.type, albedo=tuple(b.albedo), alpha=b.alpha, intIOR=b.intIOR, extIOR=b.extIOR, ks=b.ks),
                     emitter=dict(type=e.type, radiance=tuple(e.radiance)))
 
-    def render(self, device=0, tile_rank=0, tile_ranks=1, gpus=1):
-        """gpus > 1: devices device..device+gpus-1 behind ONE context (nb_create_multi), the path of `nori --gpus N`."""
+    def render(self, device=0, tile_rank=0, tile_ranks=1, gpus=1, accel_cache=None, srgb8=False):
+        """gpus > 1: devices device..device+gpus-1 behind ONE context (nb_create_multi), the path of `nori --gpus N`.
+        accel_cache: file caching the built hierarchy (`nori --cache`).  srgb8=True also returns the 8-bit tonemapped image
+        twice -- from the device kernel and from the host loop -- as (film, stats, dev8, host8)."""
         i = self.info()
         b = i["border"]
         film = np.zeros((i["height"] + 2 * b, i["width"] + 2 * b, 4), dtype=np.float32)
         st = abi.Stats()
-        if gpus > 1:
-            rc = lib().nori_host_render_gpus(self.h, device, gpus, film.ctypes.data_as(C.c_void_p), C.byref(st))
+        if gpus > 1 or accel_cache or srgb8:
+            d8 = np.zeros((i["height"], i["width"], 3), dtype=np.uint8) if srgb8 else None
+            h8 = np.zeros((i["height"], i["width"], 3), dtype=np.uint8) if srgb8 else None
+            rc = lib().nori_host_render_gpus(self.h, device, gpus, os.fspath(accel_cache).encode() if accel_cache else None,
+                                             film.ctypes.data_as(C.c_void_p), d8.ctypes.data_as(C.c_void_p) if srgb8 else None,
+                                             h8.ctypes.data_as(C.c_void_p) if srgb8 else None, C.byref(st))
         else:
             rc = lib().nori_host_render(self.h, device, tile_rank, tile_ranks, film.ctypes.data_as(C.c_void_p), C.byref(st))
         if rc:
             raise abi.NoriError(lib().nori_host_last_error().decode())
-        return film, st
+        return (film, st, d8, h8) if srgb8 else (film, st)
 
 
 # ----------------------------------------------------------------------------- XML writer (scene description -> Nori XML + OBJ)

@@ -24,6 +24,8 @@ const char *nb_last_error(void) { return g_err; }
 nb_ctx *nb_create(int device) { (void) device; return (nb_ctx *) calloc(1, sizeof(nb_ctx)); }
 void nb_destroy(nb_ctx *c) { free(c); }
 nb_ctx *nb_create_multi(const int *devices, int ndev) { (void) ndev; return nb_create(devices ? devices[0] : 0); }
+int nb_set_accel_cache(nb_ctx *c, const char *path) { (void) c; (void) path; return 0; }
+int nb_last_film_to_srgb8(nb_ctx *c, uint8_t *rgb8) { (void) c; (void) rgb8; return 1; }
 int nb_set_option(nb_ctx *c, const char *k, int64_t v) { (void) c; (void) k; (void) v; return 0; }
 int nb_add_mesh(nb_ctx *c, const float *V, uint32_t nv, const float *N, const float *UV, const uint32_t *F, uint32_t nf,
                 const nb_bsdf_desc *b, const nb_emitter_desc *e) { (void) c; (void) V; (void) nv; (void) N; (void) UV; (void) F; (void) nf; (void) b; (void) e; return 0; }

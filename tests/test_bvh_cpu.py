@@ -190,3 +190,35 @@ def test_emulated_device_walk_matches_brute_force(oracle):
             n_hit += 1
             assert np.float32(t) == hits["t"][i] and np.float32(u) == hits["u"][i] and np.float32(v) == hits["v"][i], i
     assert n_hit > 50
+
+
+def test_hierarchy_cache_round_trip(tmp_path):
+    """SURVEY 8f row 3 / VERDICT r1 item 9: the built BVH (nodes + leaf-ordered triangles) is cached on disk, keyed on the
+    geometry and the build parameters; a hit returns the very same arrays, anything else rebuilds."""
+    m = S.ajax_standin(2)
+    path = tmp_path / "scene.nbbvh"
+    n0, t0, i0 = abi.debug_bvh_cache(m.V, m.F, path)              # miss: builds and writes
+    assert not i0["hit"] and path.exists() and path.stat().st_size == 64 + n0.nbytes + t0.nbytes
+    ref_nodes, ref_tris, ref_info = abi.debug_build_bvh(m.V, m.F)
+    assert n0.tobytes() == ref_nodes.tobytes() and t0.tobytes() == ref_tris.tobytes()
+    n1, t1, i1 = abi.debug_bvh_cache(m.V, m.F, path)              # hit: same bytes, no build
+    assert i1["hit"] and n1.tobytes() == n0.tobytes() and t1.tobytes() == t0.tobytes()
+    assert {k: i1[k] for k in ("nodes", "tris", "top_nodes", "depth")} == {k: ref_info[k] for k in ("nodes", "tris", "top_nodes", "depth")}
+    # other build parameters or other geometry: the key differs, the file is rebuilt
+    _, _, i2 = abi.debug_bvh_cache(m.V, m.F, path, max_leaf=4)
+    assert not i2["hit"]
+    _, _, i3 = abi.debug_bvh_cache(m.V, m.F, path, max_leaf=4)
+    assert i3["hit"]
+    V2 = m.V.copy(); V2[17, 1] += 1e-3
+    n4, t4, i4 = abi.debug_bvh_cache(V2, m.F, path, max_leaf=4)
+    assert not i4["hit"]
+    # a damaged file (flipped payload byte, truncation) misses and is replaced
+    raw = bytearray(path.read_bytes()); raw[len(raw) // 2] ^= 0x40; path.write_bytes(bytes(raw))
+    n5, t5, i5 = abi.debug_bvh_cache(V2, m.F, path, max_leaf=4)
+    assert not i5["hit"] and n5.tobytes() == n4.tobytes()
+    path.write_bytes(path.read_bytes()[:1000])
+    assert not abi.debug_bvh_cache(V2, m.F, path, max_leaf=4)[2]["hit"]
+    assert abi.debug_bvh_cache(V2, m.F, path, max_leaf=4)[2]["hit"]
+    # a read-only location is not an error: the build just is not cached
+    n6, _, i6 = abi.debug_bvh_cache(V2, m.F, "/proc/nope/scene.nbbvh", max_leaf=4)
+    assert not i6["hit"] and n6.tobytes() == n4.tobytes()

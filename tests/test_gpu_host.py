@@ -95,3 +95,57 @@ def test_block_api_shards_merge_to_the_full_frame():
     assert S.rel_l2(film.cpu().numpy(), full) < 1e-6
     assert S.rel_l2(film2.cpu().numpy(), full) < 1e-6
     assert S.rel_l2(MG.merge_blocks_numpy(per_rank, W, H, b), full) < 1e-6
+
+
+def test_device_tonemap_bytes_equal_host_loop_and_png(tmp_path, oracle):
+    """SURVEY 8f row 4: normalise + sRGB tonemap + 8-bit pack run on the device (film_to_srgb8_kernel) and feed the PNG writer;
+    the bytes equal the host loop's (Bitmap::toSRGB8: ref src/common.cpp:166-180, src/bitmap.cpp:100-110)."""
+    sc = S.config_cbox(160, 120, 16, S.INT_PATH_MIS)      # dark corners (linear segment) and bright light (clamped) in one image
+    path = host.write_xml(sc, str(tmp_path), "cbox")
+    hs = host.HostScene(path)
+    film, st, dev8, host8 = hs.render(0, srgb8=True)
+    assert dev8.shape == (120, 160, 3) and dev8.max() == 255 and dev8.min() < 30
+    assert np.array_equal(dev8, host8)
+    with abi.Context(0) as ctx:
+        ctx.load(sc)
+        f2, _ = ctx.render()
+        assert np.array_equal(ctx.last_film_to_srgb8(), dev8)
+        ctx.configure(sc)                                  # a new camera / filter invalidates the device film
+        with pytest.raises(abi.NoriError, match="no film on the device"):
+            ctx.last_film_to_srgb8()
+    if not os.path.exists(host.CLI_PATH):
+        from nori_b200 import build as nb_build
+        nb_build.build_host(force=True)
+    r = subprocess.run([host.CLI_PATH, path, "--no-gui"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    import cv2
+    img = cv2.imread(str(tmp_path / "cbox.png"))           # BGR
+    assert np.array_equal(img[..., ::-1], dev8)
+
+
+def test_hierarchy_cache_on_the_render_path(tmp_path, oracle):
+    """the built BVH is cached on disk (`nori --cache`, nb_set_accel_cache); a hit skips the build and
+    renders the same film."""
+    sc = S.Scene([S.ajax_standin(3)], S.Camera(S.lookat(**S._AJAX_CAM).astype(np.float32), 30.0, 160, 120), S.INT_AO, 4)
+    cache = tmp_path / "scene.nbbvh"
+    with abi.Context(0) as ctx:
+        ctx.set_accel_cache(cache)
+        ctx.load(sc)
+        assert not ctx.accel_cache_hit and cache.exists()
+        ref, st = ctx.render()
+    with abi.Context(0) as ctx:
+        ctx.set_accel_cache(cache)
+        ctx.load(sc)
+        assert ctx.accel_cache_hit and ctx.build_stats()["seconds"] == 0.0
+        film, st2 = ctx.render()
+        assert st2.rays == st.rays and S.rel_l2(film, ref) < 1e-6
+        ctx.set_option("max_leaf", 2)                      # other build parameters: other key
+        ctx.load(sc)
+        assert not ctx.accel_cache_hit
+        film, st3 = ctx.render()
+        assert st3.rays == st.rays and S.rel_l2(film, ref) < 1e-6
+    path = host.write_xml(sc, str(tmp_path), "ajax")
+    hs = host.HostScene(path)
+    f1, s1 = hs.render(0, accel_cache=tmp_path / "ajax.nbbvh")
+    f2, s2 = hs.render(0, accel_cache=tmp_path / "ajax.nbbvh")
+    assert (tmp_path / "ajax.nbbvh").exists() and s1.rays == s2.rays and S.rel_l2(f2, f1) < 1e-6
