@@ -19,7 +19,7 @@ exit $?
 fi
 set -x
 nvidia-smi -L; nproc
-timeout 900 python -m pytest tests/test_gpu_entry_points.py tests/test_gpu_full_size.py tests/test_gpu_multi.py -q -x 2>&1 | tail -15
+(time timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25)
 NB_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_zzz_gpu_deferred_engine.py -q 2>&1 | tail -15
 bash tools/ab_variants.sh "default _l256 _compact default _l256 _compact" "ajax-ao cbox-mis"
 bash tools/ab_variants.sh "default _l256" "random10m-ao" "--spp 4"
