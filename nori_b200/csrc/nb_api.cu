@@ -289,7 +289,123 @@ int render_blocks_deferred(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_sta
     return 0;
 }
 
+// ---- wavefront engine (nb_wave.cu): launchers with C linkage, RenderParams passed as bytes
+extern "C" cudaError_t nb_wv_launch_logic(const void *params, size_t bytes, int integ, cudaStream_t s);
+extern "C" cudaError_t nb_wv_launch_trace(const void *params, size_t bytes, int count, int grid, cudaStream_t s);
+extern "C" cudaError_t nb_wv_occupancy(int count, int *blocks_trace);
+extern "C" int nb_wv_columns(void);
+
+// Same contract as render_blocks.  A pool of wf_pool path slots lives in device memory; one ITERATION is one logic launch
+// (every slot: splat + regenerate, or one integrator step; rays go to the extension / occlusion queues) and one trace launch
+// (persistent warps with dynamic fetch drain both queues).  The host enqueues `wf_check` iterations at a time and then reads
+// the live-slot counter; the loop ends when no slot holds a path.  This call therefore synchronises with the stream.
+int render_blocks_wave(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, int *n_tiles_out) {
+    if (c->seed_mode == NB_SEED_PER_BLOCK) return render_blocks(c, blocks_out, s, st, n_tiles_out);   // sequential streams: fused engine
+    if (ensure_device(c)) return 1;
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    nb::RenderParams P;
+    memset(&P, 0, sizeof P);
+    if (fill_scene(c, P.sc)) return 1;
+    if (c->integ.type < NB_INT_NORMALS || c->integ.type > NB_INT_SIMPLE) return fail("unsupported integrator type %d (no CPU fallback)", c->integ.type);
+    if (c->integ.type == NB_INT_SIMPLE && !c->have_light) return fail("the simple integrator needs nb_set_point_light");
+    memcpy(P.light_pos, c->light_pos, sizeof P.light_pos); memcpy(P.light_energy, c->light_energy, sizeof P.light_energy);
+    memcpy(P.s2c, c->s2c, sizeof P.s2c); memcpy(P.c2w, c->c2w, sizeof P.c2w);
+    P.W = c->W; P.H = c->H; P.invW = 1.0f / (float) c->W; P.invH = 1.0f / (float) c->H;
+    P.nearClip = c->nearClip; P.farClip = c->farClip;
+    memcpy(P.ftable, c->ftable, sizeof P.ftable);
+    P.fradius = c->fradius; P.lookup = NB_FILTER_RESOLUTION / c->fradius; P.border = c->border;
+    P.spp = c->spp; P.seed_mode = c->seed_mode; P.seed = c->seed;
+    P.integrator = c->integ.type; P.rr_start = c->integ.rr_start > 0 ? c->integ.rr_start : 3;
+    P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
+    P.tile_rank = c->tile_rank; P.tile_nranks = c->tile_nranks;
+    P.n_my_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, &P.ntx, &P.nty);
+    P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
+    if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
+    P.wf_chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(c->opt_chunk > 0 ? c->opt_chunk : 8, std::min<int64_t>(8, c->spp)));
+    P.chunk = P.wf_chunk;
+    P.nchunks = (c->spp + P.wf_chunk - 1) / P.wf_chunk;
+    P.wf_total = (unsigned long long) P.n_my_tiles * 32ull * P.nchunks * 32ull * P.wf_chunk;
+    // pool: as many slots as asked for, never more than there are samples, a multiple of 128
+    unsigned long long pool = (unsigned long long) std::max<int64_t>(128, c->opt_wf_pool);
+    pool = std::min<unsigned long long>(pool, std::max<unsigned long long>(P.wf_total, 128ull));
+    pool = (pool + 127ull) / 128ull * 128ull;
+    P.wf_pool = (uint32_t) pool;
+    const int ncols = nb_wv_columns();
+    if (pool > c->wf_cap) {
+        if (c->wf_cols) cudaFree(c->wf_cols);
+        if (c->wf_ext) cudaFree(c->wf_ext);
+        if (c->wf_shadow) cudaFree(c->wf_shadow);
+        c->wf_cols = nullptr; c->wf_ext = nullptr; c->wf_shadow = nullptr; c->wf_cap = 0;
+        CK(cudaMalloc(&c->wf_cols, sizeof(float4) * (size_t) ncols * pool));
+        CK(cudaMalloc(&c->wf_ext, sizeof(uint32_t) * pool));
+        CK(cudaMalloc(&c->wf_shadow, sizeof(float4) * 3 * pool));
+        c->wf_cap = pool;
+    }
+    if (!c->wf_ctr) { CK(cudaMalloc(&c->wf_ctr, sizeof(uint32_t) * 8)); CK(cudaMallocHost(&c->wf_ctr_h, sizeof(uint32_t) * 8)); }
+    P.wf_cols = c->wf_cols; P.wf_ext = c->wf_ext; P.wf_ctr = c->wf_ctr; P.occ_queue = c->wf_shadow; P.occ_capacity = P.wf_pool;
+    P.tail_lanes = (int32_t) c->opt_occ_tail;
+    const size_t blk_elems = (size_t) P.n_my_tiles * P.block_edge * P.block_edge;
+    if (!blocks_out) {
+        if (blk_elems > c->blocks_cap) {
+            if (c->blocks) cudaFree(c->blocks);
+            c->blocks = nullptr; c->blocks_cap = 0;
+            CK(cudaMalloc(&c->blocks, sizeof(float4) * (blk_elems ? blk_elems : 1)));
+            c->blocks_cap = blk_elems;
+        }
+        blocks_out = c->blocks;
+    }
+    P.blocks = blocks_out;
+    P.counters = c->counters;
+    const bool count = c->opt_count != 0;
+    int occ_t = 0;
+    cudaError_t oe = nb_wv_occupancy(count ? 1 : 0, &occ_t);
+    if (oe != cudaSuccess) return fail("occupancy query failed: %s", cudaGetErrorString(oe));
+    if (occ_t < 1) return fail("wavefront trace kernel does not fit on an SM");
+    if (c->opt_blocks_per_sm > 0) occ_t = (int) std::min<int64_t>(occ_t, c->opt_blocks_per_sm);
+    // persistent trace grid: a whole number of CTAs per SM, but no more warps than rays to fetch 32 at a time
+    const int grid_t = (int) std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long) c->sm_count * occ_t, (pool + 127ull) / 128ull));
+
+    CK(cudaEventRecord(c->ev[0], s));
+    CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s));
+    CK(cudaMemsetAsync(c->wf_ctr, 0, sizeof(uint32_t) * 8, s));
+    CK(cudaMemsetAsync(c->wf_cols + (size_t) 4 * pool, 0, sizeof(float4) * pool, s));      // column 4 holds the slot state: all empty
+    if (blk_elems) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));
+    CK(cudaEventRecord(c->ev[1], s));
+    unsigned long long launches = 0;
+    const int check = (int) std::max<int64_t>(1, c->opt_wf_check);
+    bool done = P.n_my_tiles == 0;
+    for (long long it = 0; !done; ) {
+        for (int k = 0; k < check; ++k, ++it) {
+            CK(cudaMemsetAsync(c->wf_ctr + 2, 0, sizeof(uint32_t) * 5, s));      // queue lengths, fetch cursors, live slots; the sample cursor keeps running
+            cudaError_t e = nb_wv_launch_logic(&P, sizeof P, c->integ.type, s);
+            if (e != cudaSuccess) return fail("wavefront logic launch failed: %s", cudaGetErrorString(e));
+            e = nb_wv_launch_trace(&P, sizeof P, count ? 1 : 0, grid_t, s);
+            if (e != cudaSuccess) return fail("wavefront trace launch failed: %s", cudaGetErrorString(e));
+            launches += 2;
+        }
+        CK(cudaMemcpyAsync(c->wf_ctr_h, c->wf_ctr, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (c->wf_ctr_h[7]) return fail("device watchdog fired in the wavefront trace kernel (results invalid)");
+        if (c->wf_ctr_h[6] == 0) done = true;                  // no slot holds a path after the last logic pass
+        if (it > 4000000) return fail("wavefront engine: no progress after %lld iterations", it);
+    }
+    CK(cudaEventRecord(c->ev[2], s));
+    if (n_tiles_out) *n_tiles_out = P.n_my_tiles;
+    if (st) {
+        memset(st, 0, sizeof *st);
+        unsigned long long ns = 0;
+        for (int k = 0; k < P.n_my_tiles; ++k) {
+            int tile_id = c->tile_rank + k * c->tile_nranks, bx = tile_id % P.ntx, by = tile_id / P.ntx;
+            ns += (unsigned long long) std::min(32, c->W - bx * 32) * std::min(32, c->H - by * 32);
+        }
+        st->samples = ns * c->spp;
+        st->launches = launches;
+    }
+    return 0;
+}
+
 int render_tiles(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, int *n_tiles_out) {
+    if (c->opt_engine == 2) return render_blocks_wave(c, blocks_out, s, st, n_tiles_out);
     return c->opt_engine == 1 ? render_blocks_deferred(c, blocks_out, s, st, n_tiles_out) : render_blocks(c, blocks_out, s, st, n_tiles_out);
 }
 
@@ -423,6 +539,11 @@ void nb_destroy(nb_ctx *c) {
     if (c->blocks) cudaFree(c->blocks);
     if (c->film) cudaFree(c->film);
     if (c->occ_queue) cudaFree(c->occ_queue);
+    if (c->wf_cols) cudaFree(c->wf_cols);
+    if (c->wf_ext) cudaFree(c->wf_ext);
+    if (c->wf_shadow) cudaFree(c->wf_shadow);
+    if (c->wf_ctr) cudaFree(c->wf_ctr);
+    if (c->wf_ctr_h) cudaFreeHost(c->wf_ctr_h);
     if (c->counters) cudaFree(c->counters);
     if (c->counters_h) cudaFreeHost(c->counters_h);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -976,7 +1097,9 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
         if (value != 0) return fail("option \"tail\" needs a library built with -DNB_TAIL_CUT=1 (this build walks every ray to completion)");
 #endif
     }
-    else if (k == "engine") { if (value != 0 && value != 1) return fail("engine must be 0 (fused) or 1 (deferred occlusion)"); c->opt_engine = value; }
+    else if (k == "engine") { if (value < 0 || value > 2) return fail("engine must be 0 (fused), 1 (deferred occlusion) or 2 (wavefront)"); c->opt_engine = value; }
+    else if (k == "wf_pool") { if (value < 128 || value > (1ll << 28)) return fail("wf_pool must be in [128, 2^28]"); c->opt_wf_pool = value; }
+    else if (k == "wf_check") { if (value < 1 || value > 1024) return fail("wf_check must be in [1, 1024]"); c->opt_wf_check = value; }
     else if (k == "occ_mb") { if (value < 1 || value > 65536) return fail("occ_mb must be in [1, 65536]"); c->opt_occ_mb = value; }
     else if (k == "occ_tail") { if (value < 0 || value > 31) return fail("occ_tail must be in [0, 31]"); c->opt_occ_tail = value; }
     else if (k == "max_leaf") { c->opt_max_leaf = value; c->built = false; }

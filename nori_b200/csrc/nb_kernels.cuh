@@ -101,6 +101,13 @@ struct RenderParams {
     float4 *occ_queue;              // 4 x float4 per queued occlusion ray (OccRay)
     uint32_t occ_capacity;          // rays the queue holds
     int32_t slot_base;              // first owned-tile slot of this slice
+    // wavefront engine (nb_wave.cu / nb_wave.cuh; unused by the other kernels)
+    float4 *wf_cols;                // path pool, structure of arrays: kWfCols columns of wf_pool float4 each
+    uint32_t *wf_ext;               // queue of pool slots whose extension ray waits to be traced
+    uint32_t *wf_ctr;               // engine counters (nb_wave.cuh: WF_*)
+    uint32_t wf_pool;               // path slots (multiple of 128)
+    uint32_t wf_chunk;              // samples per work unit (<= 8)
+    unsigned long long wf_total;    // sample indices to hand out (virtual: ragged tiles / last chunk included)
 };
 
 // ------------------------------------------------------------------ traversal state (per lane)
@@ -409,7 +416,25 @@ __device__ __forceinline__ void splat(const RenderParams &P, int tile_slot, int 
     }
 }
 
-#if NB_DEFER_SHADOW
+#if NB_DEFER_SHADOW == 2
+// Wavefront engine: one thread per pool slot (nb_wave.cuh: wf_logic_kernel).  An occlusion ray goes to the shadow queue with
+// the radiance it would add to the path and the slot it belongs to; wf_trace_kernel adds it to the slot's L if unoccluded.
+// A path emits at most one such ray per iteration, so the queue (one entry per slot) cannot overflow.
+__device__ __forceinline__ bool occ_push(const RenderParams &P, const Ray &r, V3 contrib, float, float, int) {
+    const unsigned mask = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if ((int) lane == leader) base = atomicAdd(&P.wf_ctr[3], (unsigned) __popc(mask));     // WF_SHADOW_COUNT
+    base = __shfl_sync(mask, base, leader);
+    const unsigned idx = base + (unsigned) __popc(mask & ((1u << lane) - 1u));
+    float4 *q = P.occ_queue + (size_t) idx * 3u;
+    q[0] = make_float4(r.ox, r.oy, r.oz, r.mint);
+    q[1] = make_float4(r.dx, r.dy, r.dz, r.maxt);
+    q[2] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(blockIdx.x * blockDim.x + threadIdx.x));
+    return true;
+}
+#elif NB_DEFER_SHADOW
 // The filter is linear, so a sample's film contribution may be splatted in pieces: the path's own radiance with the
 // filter weight (splat above), and each unoccluded next-event / ambient-occlusion term later with weight 0.
 __device__ __forceinline__ void splat_contrib(const RenderParams &P, int tile_slot, float sx, float sy, V3 value) {
@@ -918,7 +943,7 @@ __global__ void __launch_bounds__(128) li_samples_kernel(const __grid_constant__
     atomicAdd(&P.counters[4], (unsigned long long) n_hits);
 }
 
-#if NB_DEFER_SHADOW
+#if NB_DEFER_SHADOW == 1
 // ------------------------------------------------------------------ occlusion kernel of the deferred engine
 // Traces the queued occlusion rays (any hit) and splats the contribution of the unoccluded ones.  Persistent warps with
 // dynamic fetch: a lane keeps its walk (node, stack) across refills; the warp leaves the walk as soon as at most

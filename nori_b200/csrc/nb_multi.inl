@@ -14,6 +14,7 @@
 // (torch's bundled one) shares it instead of loading a second.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <thread>
 
 namespace nbm {
 
@@ -157,9 +158,23 @@ int render_group(nb_ctx *c, float4 *film, cudaStream_t s0, nb_stats *st) {
         }
     }
     // ---- every device renders its tiles (asynchronous launches, one stream per device)
-    for (nb_ctx *x : L) {
-        cudaStream_t s = (x == c) ? s0 : x->stream;
-        if (render_tiles(x, x->comm_rank == 0 ? x->gather : x->send_blocks, s, &x->last_st, nullptr)) return 1;
+    if (L.size() > 1 && c->opt_engine == 2) {
+        // the wavefront engine's host loop synchronises with its stream: one host thread per device, or they would run in turn
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(L.size());
+        for (size_t i = 0; i < L.size(); ++i)
+            th.emplace_back([&, i] {
+                nb_ctx *x = L[i];
+                cudaStream_t s = (x == c) ? s0 : x->stream;
+                if (render_tiles(x, x->comm_rank == 0 ? x->gather : x->send_blocks, s, &x->last_st, nullptr)) errs[i] = nb_last_error();
+            });
+        for (auto &t : th) t.join();
+        for (const std::string &e : errs) if (!e.empty()) return fail("%s", e.c_str());
+    } else {
+        for (nb_ctx *x : L) {
+            cudaStream_t s = (x == c) ? s0 : x->stream;
+            if (render_tiles(x, x->comm_rank == 0 ? x->gather : x->send_blocks, s, &x->last_st, nullptr)) return 1;
+        }
     }
     // ---- ONE exchange per frame: finished ImageBlocks to rank 0
     if (per_rank) {

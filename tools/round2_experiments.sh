@@ -29,9 +29,13 @@ bash tools/ab_variants.sh "_p10 _p9" "cbox-mis"
 NORI_B200_LIB=nori_b200/lib/libnori_b200_tail.so TAILS="0 2 4 8 12" timeout 120 python tools/tail_sweep.py ajax-ao cbox-mis
 # deferred-occlusion engine (nb_wavefront.cu): A/B against the fused kernel, refill threshold sweep
 for w in ajax-ao cbox-mis; do
-  for o in "engine=0" "engine=1" "engine=1 --opt occ_tail=12" "engine=1 --opt occ_tail=24" "engine=1 --opt occ_tail=28"; do
+  for o in "engine=0" "engine=1" "engine=1 --opt occ_tail=12" "engine=1 --opt occ_tail=24" "engine=1 --opt occ_tail=28" \
+           "engine=2" "engine=2 --opt wf_pool=1048576" "engine=2 --opt wf_pool=4194304" "engine=2 --opt wf_pool=8388608 --opt wf_check=8" "engine=2 --opt occ_tail=12" "engine=2 --opt occ_tail=26"; do
     timeout 300 python bench.py --workload $w --steps 8 --warmup 3 --no-cpu-baseline --no-configs --opt $o 2>gpurun_out/ab_err.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ENG','$w','[$o]',round(d['ms_per_step'],3),round(d['value'],1))" || tail -3 gpurun_out/ab_err.log
   done
+done
+for o in "engine=0" "engine=1" "engine=2" "engine=2 --opt wf_pool=8388608"; do
+  timeout 300 python bench.py --workload ajax-rough --spp 128 --steps 5 --warmup 3 --no-cpu-baseline --no-configs --opt $o 2>gpurun_out/ab_err.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ENG','ajax-rough128','[$o]',round(d['ms_per_step'],3),round(d['value'],1))" || tail -3 gpurun_out/ab_err.log
 done
 # the whole default bench line (all five BASELINE configs) + the CPU arm
 (time timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r2_a.json 2> gpurun_out/bench_r2_a.err); tail -c 600 gpurun_out/bench_r2_a.err; head -c 3000 gpurun_out/bench_r2_a.json
