@@ -699,9 +699,9 @@ static int build_accel_local(nb_ctx *c) {
     const uint32_t bfs = c->opt_bfs_nodes < 0 ? nb::kSiblingPairs : (uint32_t) c->opt_bfs_nodes;
     // on-disk hierarchy cache (nb_set_accel_cache): keyed on every vertex / index the builder reads + the build parameters
     uint64_t key = 0; bool hit = false;
-    if (!c->accel_cache.empty()) { key = nb::bvh_cache_key(in, (int) c->opt_max_leaf, bfs); hit = nb::bvh_cache_load(c->accel_cache.c_str(), key, out); }
+    if (!c->accel_cache.empty()) { key = nb::bvh_cache_key(in, (int) c->opt_max_leaf, bfs, nb::kStack); hit = nb::bvh_cache_load(c->accel_cache.c_str(), key, out); }
     if (!hit) {
-        nb::build_bvh(in, out, (int) c->opt_max_leaf, bfs, 0);
+        nb::build_bvh(in, out, (int) c->opt_max_leaf, bfs, 0, nb::kStack);
         if (!c->accel_cache.empty()) nb::bvh_cache_save(c->accel_cache.c_str(), key, out);
     }
     c->accel_cache_hit = hit;

@@ -63,6 +63,7 @@ struct Builder {
     std::atomic<uint32_t> nnodes{0};
     std::atomic<int> threads_free{0};
     int max_leaf;
+    int max_depth = 64;              // the walk's per-lane stack: every leaf must end up shallower than this
 
     uint32_t alloc() { return nnodes.fetch_add(1); }
 
@@ -88,7 +89,11 @@ struct Builder {
 
         int best_axis = -1, best_bin = -1;
         float best_cost = kInf;
-        if (depth < 44) {   // beyond that: balanced index splits, so the traversal stack (64) can never overflow
+        // A subtree of n triangles finished by balanced index splits is at most ceil(log2 n) + 1 levels deep, so a SAH split
+        // is taken only while its children could still be finished that way below max_depth: the traversal stack can never
+        // overflow, whatever the geometry (depth + 2 + ceil(log2 n) < max_depth).
+        int lg = 0; while ((1u << lg) < n) ++lg;
+        if (depth + 2 + lg < max_depth) {
             Box bins[3][kBins]; uint32_t cnt[3][kBins];
             float scale[3];
             for (int a = 0; a < 3; ++a) {
@@ -190,7 +195,7 @@ inline float as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 }  // namespace
 
-void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_nodes, int nthreads) {
+void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_nodes, int nthreads, int max_depth) {
     auto t0 = std::chrono::steady_clock::now();
     max_leaf = std::min(8, std::max(1, max_leaf));
     const uint32_t n = in.nprims;
@@ -216,7 +221,7 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
 
     Builder b;
     std::vector<uint32_t> scratch(n >= Builder::kParallelNode ? n : 0);
-    b.prims = prims.data(); b.order = order.data(); b.max_leaf = max_leaf;
+    b.prims = prims.data(); b.order = order.data(); b.max_leaf = max_leaf; b.max_depth = std::max(8, max_depth);
     b.scratch = scratch.empty() ? nullptr : scratch.data();
     b.nodes.resize(n ? 2 * (size_t) n : 1);
     if (nthreads <= 0) nthreads = (int) std::thread::hardware_concurrency();
@@ -378,9 +383,9 @@ inline uint64_t fnv1a(const void *data, size_t n, uint64_t h) {
 }
 }  // namespace
 
-uint64_t bvh_cache_key(const BvhInput &in, int max_leaf, uint32_t bfs_nodes) {
+uint64_t bvh_cache_key(const BvhInput &in, int max_leaf, uint32_t bfs_nodes, int max_depth) {
     uint64_t h = 0xcbf29ce484222325ull;
-    const uint32_t params[4] = { in.nprims, (uint32_t) max_leaf, bfs_nodes, 2u /* layout version */ };
+    const uint32_t params[5] = { in.nprims, (uint32_t) max_leaf, bfs_nodes, 2u /* layout version */, (uint32_t) max_depth };
     h = fnv1a(params, sizeof params, h);
     uint32_t max_v = 0;
     for (uint32_t i = 0; i < in.nprims; ++i) for (int k = 0; k < 3; ++k) max_v = std::max(max_v, in.faces[4 * (size_t) i + k]);

@@ -55,7 +55,10 @@ namespace nb {
 #ifndef NB_WATCHDOG_CYCLES
 #define NB_WATCHDOG_CYCLES 40000000000LL   // ~20 s at 1.9 GHz
 #endif
-constexpr int kStack = 64;          // builder guarantees depth < 64 (nb_bvh.cpp)
+#ifndef NB_STACK
+#define NB_STACK 64
+#endif
+constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
 constexpr int kBlockEdgeMax = 32 + 2 * 8;
 
 struct SceneDev {

@@ -5,12 +5,14 @@
 #   _compact : NB_COMPACT_PATH=1  -- tile rectangle re-derived at splat time (fewer spills)
 #   _tail    : NB_TAIL_CUT=1      -- resumable walks; run time option "tail"
 #   _p10/_p9 : register cap of the path tracers (default 11 CTAs/SM = 40 registers)
+#   _s32     : NB_STACK=32        -- per-lane traversal stack of 32 entries (half the local-memory footprint; host SAH trees only)
 if [ "$1" = "--build" ]; then
 python - <<'PY'
 from concurrent.futures import ThreadPoolExecutor
 from nori_b200 import build
 V = [("", ()), ("_l256", ("-DNB_LDG256=1",)), ("_compact", ("-DNB_COMPACT_PATH=1",)), ("_tail", ("-DNB_TAIL_CUT=1",)),
-     ("_p10", ("-DNB_MIN_BLOCKS_PATH=10",)), ("_p9", ("-DNB_MIN_BLOCKS_PATH=9",))]
+     ("_p10", ("-DNB_MIN_BLOCKS_PATH=10",)), ("_p9", ("-DNB_MIN_BLOCKS_PATH=9",)), ("_s32", ("-DNB_STACK=32",)),
+     ("_l256s32", ("-DNB_LDG256=1", "-DNB_STACK=32"))]
 with ThreadPoolExecutor(2) as ex:
     print(list(ex.map(lambda v: build.build_cuda(force=True, variant=v[0], extra_flags=v[1]), V)))
 print(build.build_host(force=True))
@@ -24,7 +26,8 @@ NB_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_zzz_gpu_deferred_en
 bash tools/ab_variants.sh "default _l256 _compact default _l256 _compact" "ajax-ao cbox-mis"
 bash tools/ab_variants.sh "default _l256" "random10m-ao" "--spp 4"
 bash tools/ab_variants.sh "default _l256 _p10 _p9" "ajax-rough" "--spp 128"
-bash tools/ab_variants.sh "_p10 _p9" "cbox-mis"
+bash tools/ab_variants.sh "_p10 _p9 _s32 _l256s32" "cbox-mis"
+bash tools/ab_variants.sh "_s32 _l256s32" "ajax-ao"
 # a walk that never ends must not take the box with it (device watchdog + timeout)
 NORI_B200_LIB=nori_b200/lib/libnori_b200_tail.so TAILS="0 2 4 8 12" timeout 120 python tools/tail_sweep.py ajax-ao cbox-mis
 # deferred-occlusion engine (nb_wavefront.cu): A/B against the fused kernel, refill threshold sweep
