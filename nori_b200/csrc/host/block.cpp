@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // block.cpp -- ImageBlock / BlockGenerator / Bitmap (ref: src/block.cpp:15-152, src/bitmap.cpp:69-122).
 #include <fstream>
 #include "nori/block.h"

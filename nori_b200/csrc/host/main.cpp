@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // main.cpp -- `nori <scene.xml>` command line (ref: src/main.cpp:150-246).  --no-gui / --threads are accepted for
 // compatibility and ignored (there is no GUI and no TBB on this path); --device N selects the GPU, --gpus N
 // renders on N devices (tiles sharded tile_id % N, finished ImageBlocks gathered over NCCL, merged on the first device),

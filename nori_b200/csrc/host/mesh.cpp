@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // mesh.cpp -- Mesh base class + Wavefront OBJ loader plugin "obj" (ref: src/mesh.cpp:16-29,96-123, src/obj.cpp:19-163).
 #include <fstream>
 #include <sstream>

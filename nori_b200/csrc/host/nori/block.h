@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // block.h -- ImageBlock: weighted RGBA film storage incl. border (ref: include/nori/block.h:31-112, src/block.cpp:15-51).
 // On this path the block is FILLED by the GPU (nb_render writes the byte-compatible storage); the host keeps the
 // constructor (filter tabulation through the host plugin's eval()), toBitmap and the BlockGenerator for API parity.

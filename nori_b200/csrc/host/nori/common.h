@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // common.h -- host-side basics of the Nori mirror (namespace, exception, constants, string helpers).
 // Mirrors the public surface of ref: include/nori/common.h (NoriException 135-140, Epsilon 38, constants 41-49,
 // helpers 142-253) without Eigen / tinyformat, neither of which is available.

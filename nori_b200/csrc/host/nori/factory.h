@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // factory.h -- NoriObjectFactory and NORI_REGISTER_CLASS (ref: include/nori/object.h:100-149); included by object.h.
 // Plugins are translation units that self-register at static-initialisation time under the name the XML scenes use.
 // NB (addition): the factory keeps the (type name, PropertyList) every object was created from, which is what lets the

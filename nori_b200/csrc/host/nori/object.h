@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // object.h -- NoriObject base class, factory and NORI_REGISTER_CLASS (ref: include/nori/object.h:20-149).
 // Same names and semantics: plugins are translation units that self-register at static-init time; the parser
 // constructs them by name, adds children, then calls activate().  One addition (marked NB): the factory records,

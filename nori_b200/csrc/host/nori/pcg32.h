@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // pcg32.h -- restatement of wjakob/pcg32 @ 70099ead (PCG-XSH-RR 64/32); the reference's ext/pcg32 submodule is
 // empty.  Pinned by the pcg-random.org known-answer vector in tests/ (via the oracle's identical restatement).
 #pragma once

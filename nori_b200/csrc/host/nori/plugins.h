@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // plugins.h -- abstract plugin interfaces of the hot path, mirroring ref: include/nori/{bsdf,emitter,integrator,
 // sampler,camera,rfilter,mesh,scene}.h.  The virtual evaluation entry points exist so that plugins written against
 // Nori's API compile unchanged; on this path radiance is evaluated by the CUDA kernels, so the shipped host plugins

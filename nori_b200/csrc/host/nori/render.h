@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // render.h -- the render() driver of the host (ref: src/main.cpp:58-148) on top of the C-ABI in include/nori_b200.h.
 #pragma once
 #include "block.h"

@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // transform.h -- homogeneous transform + inverse (ref: include/nori/transform.h:22-83).  Row-major 4x4 fp32; the
 // inverse is computed in double and rounded once (Eigen's fp32 inverse is not reproducible without Eigen).
 #pragma once

@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // vector.h -- minimal fixed-size vector / colour types standing in for the Eigen-based ones of
 // ref: include/nori/vector.h and include/nori/color.h (only what the host pipeline needs).
 #pragma once

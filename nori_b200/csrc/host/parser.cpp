@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // parser.cpp -- Nori XML scene loader (ref: src/parser.cpp:16-305) on a self-contained mini XML reader
 // (pugixml, the reference's DOM, is an empty submodule here).  Same grammar and lifecycle: properties are collected
 // into the parent's PropertyList, objects are created through NoriObjectFactory::createInstance, children are added

@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // plugins.cpp -- the host-side plugin classes of the hot path: BSDFs, area emitter, integrators, sampler, camera,
 // reconstruction filters.  Each registers under the name the reference's scenes use (NORI_REGISTER_CLASS).
 // The host objects carry PARAMETERS; radiance is evaluated by the CUDA kernels (nori_b200/csrc/nb_kernels.cuh), which

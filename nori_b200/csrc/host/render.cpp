@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // render.cpp -- host side of the drop-in boundary: everything the reference's render() (ref: src/main.cpp:58-148)
 // and Scene/Accel glue (ref: src/scene.cpp:27-53) did around the hot loop, now expressed as calls into the C-ABI.
 #include <chrono>

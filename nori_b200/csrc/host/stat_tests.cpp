@@ -1,3 +1,5 @@
+// Host mirror of the Nori educational ray tracer's interfaces (after Nori, Copyright (c) 2015 by Wenzel Jakob);
+// re-implemented here without third-party code so that plugins register and parse unchanged -- see DESIGN.md section 1.
 // stat_tests.cpp -- the statistical test objects of the scene grammar, <test type="ttest"> and <test type="chi2test">,
 // with every BSDF / integrator evaluation done by the device through the C-ABI.
 //

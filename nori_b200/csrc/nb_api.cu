@@ -129,7 +129,6 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     // Reference per-block streams are sequential by construction; only `normals` consumes a fixed number of draws per
     // sample (4), which lets the parallel kernel jump to each sample's stream position (pcg32 skip-ahead).
     P.block_stream_skip = (c->seed_mode == NB_SEED_PER_BLOCK && c->integ.type == NB_INT_NORMALS) ? 1 : 0;
-    P.tail_lanes = (int32_t) c->opt_tail;
     const bool block_mode = c->seed_mode == NB_SEED_PER_BLOCK && !P.block_stream_skip;
     const bool count = c->opt_count != 0;
     P.smem_nodes = (block_mode || count) ? 0 : (int) std::min<int64_t>(std::min<int64_t>(c->opt_smem_nodes, c->top_nodes), 3400);
@@ -152,6 +151,14 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s));
     if (blk_elems) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));
     CK(cudaEventRecord(c->ev[1], s));
+    // L2 warm-up (inside the timed region): only when the walk's arrays fit L2 with room to spare, and never for the
+    // one-thread-per-block plumbing mode
+    const size_t walk_bytes = c->nodes.bytes() + c->tris.bytes();
+    if (P.n_my_tiles > 0 && !block_mode && c->opt_prefetch != 0 && walk_bytes > 0 && walk_bytes <= (size_t) 96 << 20) {
+        nb::l2_prefetch_kernel<<<std::min(c->sm_count * 4, (int) ((walk_bytes / 4096 + 127) / 128 + 1)), 128, 0, s>>>(
+            reinterpret_cast<const char *>(c->nodes.d), c->nodes.bytes(), reinterpret_cast<const char *>(c->tris.d), c->tris.bytes());
+        CK(cudaGetLastError());
+    }
     if (P.n_my_tiles > 0) {
         switch (c->integ.type) {
             case 0: launch_render<0>(P, count, block_mode, grid, smem, s); break;
@@ -176,115 +183,6 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
         }
         st->samples = ns * c->spp;
         st->launches = P.n_my_tiles > 0 ? 1 : 0;
-    }
-    return 0;
-}
-
-// ---- deferred-occlusion engine (nb_wavefront.cu): launchers with C linkage, RenderParams passed as bytes
-extern "C" cudaError_t nb_wf_occupancy(int integ, int count, int *blocks_render, int *blocks_occlusion);
-extern "C" cudaError_t nb_wf_launch_render(const void *params, size_t bytes, int integ, int count, int grid, cudaStream_t s);
-extern "C" cudaError_t nb_wf_launch_occlusion(const void *params, size_t bytes, int grid, cudaStream_t s);
-
-// Same contract as render_blocks.  The owned tiles are rendered in slices sized so that the occlusion rays of a slice
-// normally fit the queue (a full queue is not an error: the render kernel then traces the ray itself); per slice one
-// render launch fills the queue and one occlusion launch drains it.
-int render_blocks_deferred(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, int *n_tiles_out) {
-    if (c->seed_mode == NB_SEED_PER_BLOCK) return render_blocks(c, blocks_out, s, st, n_tiles_out);   // sequential streams: fused engine
-    if (ensure_device(c)) return 1;
-    if (!c->have_camera) return fail("nb_set_camera has not been called");
-    nb::RenderParams P;
-    memset(&P, 0, sizeof P);
-    if (fill_scene(c, P.sc)) return 1;
-    if (c->integ.type < NB_INT_NORMALS || c->integ.type > NB_INT_SIMPLE) return fail("unsupported integrator type %d (no CPU fallback)", c->integ.type);
-    if (c->integ.type == NB_INT_SIMPLE && !c->have_light) return fail("the simple integrator needs nb_set_point_light");
-    memcpy(P.light_pos, c->light_pos, sizeof P.light_pos); memcpy(P.light_energy, c->light_energy, sizeof P.light_energy);
-    memcpy(P.s2c, c->s2c, sizeof P.s2c); memcpy(P.c2w, c->c2w, sizeof P.c2w);
-    P.W = c->W; P.H = c->H; P.invW = 1.0f / (float) c->W; P.invH = 1.0f / (float) c->H;
-    P.nearClip = c->nearClip; P.farClip = c->farClip;
-    memcpy(P.ftable, c->ftable, sizeof P.ftable);
-    P.fradius = c->fradius; P.lookup = NB_FILTER_RESOLUTION / c->fradius; P.border = c->border;
-    P.spp = c->spp; P.seed_mode = c->seed_mode; P.seed = c->seed;
-    P.integrator = c->integ.type; P.rr_start = c->integ.rr_start > 0 ? c->integ.rr_start : 3;
-    P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
-    P.tile_rank = c->tile_rank; P.tile_nranks = c->tile_nranks;
-    P.n_my_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, &P.ntx, &P.nty);
-    P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
-    if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
-    // queue
-    const size_t want = (size_t) c->opt_occ_mb * 1024 * 1024 / 64;
-    if (want != c->occ_cap) {
-        if (c->occ_queue) cudaFree(c->occ_queue);
-        c->occ_queue = nullptr; c->occ_cap = 0;
-        CK(cudaMalloc(&c->occ_queue, want * 64));
-        c->occ_cap = want;
-    }
-    P.occ_queue = c->occ_queue; P.occ_capacity = (uint32_t) std::min<size_t>(c->occ_cap, 0xffffffffu);
-    // slices: a path queues about one ray per bounce with next-event estimation, exactly <= 1 for ao / simple, 0 for normals
-    const double per_path = (c->integ.type == NB_INT_AO || c->integ.type == NB_INT_SIMPLE) ? 1.0 : (c->integ.type == NB_INT_NORMALS ? 0.05 : 4.0);
-    const double per_tile = 1024.0 * c->spp * per_path;
-    const int slice_tiles = (int) std::max<double>(1.0, std::min<double>((double) std::max(P.n_my_tiles, 1), (double) c->occ_cap / per_tile));
-    int64_t chunk = c->opt_chunk;
-    if (chunk <= 0) {
-        const int64_t warps = (int64_t) c->sm_count * NB_MIN_BLOCKS * 4;
-        const int64_t units1 = (int64_t) std::min(slice_tiles, std::max(P.n_my_tiles, 1)) * 32 * c->spp;
-        chunk = std::max<int64_t>(1, std::min<int64_t>(8, units1 / (16 * warps)));
-    }
-    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, c->spp));
-    P.nchunks = (c->spp + P.chunk - 1) / P.chunk;
-    const size_t blk_elems = (size_t) P.n_my_tiles * P.block_edge * P.block_edge;
-    if (!blocks_out) {
-        if (blk_elems > c->blocks_cap) {
-            if (c->blocks) cudaFree(c->blocks);
-            c->blocks = nullptr; c->blocks_cap = 0;
-            CK(cudaMalloc(&c->blocks, sizeof(float4) * (blk_elems ? blk_elems : 1)));
-            c->blocks_cap = blk_elems;
-        }
-        blocks_out = c->blocks;
-    }
-    P.blocks = blocks_out;
-    P.counters = c->counters;
-    const bool count = c->opt_count != 0;
-    int occ_r = 0, occ_o = 0;
-    cudaError_t oe = nb_wf_occupancy(c->integ.type, count ? 1 : 0, &occ_r, &occ_o);
-    if (oe != cudaSuccess) return fail("occupancy query failed: %s", cudaGetErrorString(oe));
-    if (occ_r < 1 || occ_o < 1) return fail("deferred-engine kernels do not fit on an SM");
-    if (c->opt_blocks_per_sm > 0) { occ_r = (int) std::min<int64_t>(occ_r, c->opt_blocks_per_sm); occ_o = (int) std::min<int64_t>(occ_o, c->opt_blocks_per_sm); }
-    const int grid_r = c->sm_count * occ_r, grid_o = c->sm_count * occ_o;
-
-    CK(cudaEventRecord(c->ev[0], s));
-    CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s));
-    if (blk_elems) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));
-    CK(cudaEventRecord(c->ev[1], s));
-    unsigned long long launches = 0;
-    for (int slot0 = 0; slot0 < P.n_my_tiles; slot0 += slice_tiles) {
-        const int n_slice = std::min(slice_tiles, P.n_my_tiles - slot0);
-        const unsigned long long units = (unsigned long long) n_slice * 32ULL * P.nchunks;
-        if (units > 0xffffffffULL) return fail("too many work units");
-        P.slot_base = slot0; P.n_units = (uint32_t) units;
-        if (slot0 > 0) {    // per slice: work-unit counter and queue length restart; the statistics counters keep accumulating
-            CK(cudaMemsetAsync(c->counters + 0, 0, sizeof(unsigned long long), s));
-            CK(cudaMemsetAsync(c->counters + 7, 0, sizeof(unsigned long long), s));
-        }
-        P.tail_lanes = 0;
-        cudaError_t e = nb_wf_launch_render(&P, sizeof P, c->integ.type, count ? 1 : 0, grid_r, s);
-        if (e != cudaSuccess) return fail("deferred render launch failed: %s", cudaGetErrorString(e));
-        CK(cudaMemsetAsync(c->counters + 0, 0, sizeof(unsigned long long), s));      // now the queue's fetch counter
-        P.tail_lanes = (int32_t) c->opt_occ_tail;
-        e = nb_wf_launch_occlusion(&P, sizeof P, grid_o, s);
-        if (e != cudaSuccess) return fail("occlusion launch failed: %s", cudaGetErrorString(e));
-        launches += 2;
-    }
-    CK(cudaEventRecord(c->ev[2], s));
-    if (n_tiles_out) *n_tiles_out = P.n_my_tiles;
-    if (st) {
-        memset(st, 0, sizeof *st);
-        unsigned long long ns = 0;
-        for (int k = 0; k < P.n_my_tiles; ++k) {
-            int tile_id = c->tile_rank + k * c->tile_nranks, bx = tile_id % P.ntx, by = tile_id / P.ntx;
-            ns += (unsigned long long) std::min(32, c->W - bx * 32) * std::min(32, c->H - by * 32);
-        }
-        st->samples = ns * c->spp;
-        st->launches = launches;
     }
     return 0;
 }
@@ -406,7 +304,7 @@ int render_blocks_wave(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *
 
 int render_tiles(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, int *n_tiles_out) {
     if (c->opt_engine == 2) return render_blocks_wave(c, blocks_out, s, st, n_tiles_out);
-    return c->opt_engine == 1 ? render_blocks_deferred(c, blocks_out, s, st, n_tiles_out) : render_blocks(c, blocks_out, s, st, n_tiles_out);
+    return render_blocks(c, blocks_out, s, st, n_tiles_out);
 }
 
 int merge(nb_ctx *c, const float4 *blocks, int n_tiles, int rank, int nranks, float4 *film, cudaStream_t s) {
@@ -538,7 +436,6 @@ void nb_destroy(nb_ctx *c) {
     c->dmeshes.release(); c->cdf.release(); c->emitters.release();
     if (c->blocks) cudaFree(c->blocks);
     if (c->film) cudaFree(c->film);
-    if (c->occ_queue) cudaFree(c->occ_queue);
     if (c->wf_cols) cudaFree(c->wf_cols);
     if (c->wf_ext) cudaFree(c->wf_ext);
     if (c->wf_shadow) cudaFree(c->wf_shadow);
@@ -1089,18 +986,10 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     else if (k == "smem_nodes") c->opt_smem_nodes = value;
     else if (k == "chunk") c->opt_chunk = value;
     else if (k == "count") c->opt_count = value;
-    else if (k == "tail") {
-#if NB_TAIL_CUT
-        if (value < 0 || value > 31) return fail("tail must be in [0, 31]");
-        c->opt_tail = value;
-#else
-        if (value != 0) return fail("option \"tail\" needs a library built with -DNB_TAIL_CUT=1 (this build walks every ray to completion)");
-#endif
-    }
-    else if (k == "engine") { if (value < 0 || value > 2) return fail("engine must be 0 (fused), 1 (deferred occlusion) or 2 (wavefront)"); c->opt_engine = value; }
+    else if (k == "prefetch") c->opt_prefetch = value;
+    else if (k == "engine") { if (value != 0 && value != 2) return fail("engine must be 0 (fused kernel) or 2 (wavefront)"); c->opt_engine = value; }
     else if (k == "wf_pool") { if (value < 128 || value > (1ll << 28)) return fail("wf_pool must be in [128, 2^28]"); c->opt_wf_pool = value; }
     else if (k == "wf_check") { if (value < 1 || value > 1024) return fail("wf_check must be in [1, 1024]"); c->opt_wf_check = value; }
-    else if (k == "occ_mb") { if (value < 1 || value > 65536) return fail("occ_mb must be in [1, 65536]"); c->opt_occ_mb = value; }
     else if (k == "occ_tail") { if (value < 0 || value > 31) return fail("occ_tail must be in [0, 31]"); c->opt_occ_tail = value; }
     else if (k == "max_leaf") { c->opt_max_leaf = value; c->built = false; }
     else if (k == "bfs_nodes") { c->opt_bfs_nodes = value; c->built = false; }

@@ -66,11 +66,11 @@ struct nb_ctx {
     unsigned long long *counters_h = nullptr;        // pinned
     // options
     int64_t opt_blocks_per_sm = 0, opt_smem_nodes = 0, opt_chunk = 0, opt_count = 0, opt_max_leaf = 3,
-            opt_bfs_nodes = 2048, opt_builder = 0, opt_tail = 0, opt_engine = 0, opt_occ_mb = 1024, opt_occ_tail = 20;
-    float4 *occ_queue = nullptr; size_t occ_cap = 0;   // deferred-occlusion engine: ray queue (rays)
+            opt_bfs_nodes = 2048, opt_builder = 0, opt_engine = 0, opt_occ_tail = 20;
     // wavefront engine (nb_wave.cu): path pool (structure of arrays), extension queue, occlusion queue, counters
     float4 *wf_cols = nullptr, *wf_shadow = nullptr; uint32_t *wf_ext = nullptr, *wf_ctr = nullptr, *wf_ctr_h = nullptr; size_t wf_cap = 0;
     int64_t opt_wf_pool = 1 << 21, opt_wf_check = 4;
+    int64_t opt_prefetch = 0;          // L2 warm-up of nodes + triangles before the render kernel (l2_prefetch_kernel)
     int builder_used = 0;   // 0 host SAH, 1 device LBVH
     std::string accel_cache; bool accel_cache_hit = false;   // on-disk hierarchy cache (nb_set_accel_cache)
     // ---- multi-GPU (nb_multi.inl)

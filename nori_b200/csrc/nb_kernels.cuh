@@ -40,14 +40,8 @@ namespace nb {
 #ifndef NB_PHASED_AO
 #define NB_PHASED_AO 1       // ajax-ao 9.59 -> 9.20 ms, random10m-ao 11.8 -> 11.2 ms (profiles/r1_final_summary.md)
 #endif
-#ifndef NB_TAIL_CUT
-#define NB_TAIL_CUT 0        // resumable walks + "tail" option; costs registers (cbox-mis +7 % at tail=0), gain not yet measured
-#endif
-#ifndef NB_COMPACT_PATH
-#define NB_COMPACT_PATH 0    // experiment: keep only tile_slot per lane, re-derive the tile rectangle at splat time
-#endif
-#ifndef NB_DEFER_SHADOW
-#define NB_DEFER_SHADOW 0    // 1 only in nb_wavefront.cu: occlusion rays (ao, next-event estimation, simple) go to a queue
+#ifndef NB_WAVEFRONT
+#define NB_WAVEFRONT 0       // 1 only in nb_wave.cu: occlusion rays (ao, next-event estimation, simple) go to the engine's shadow queue
 #endif
 #ifndef NB_SPLAT_HOIST
 #define NB_SPLAT_HOIST 1
@@ -98,13 +92,12 @@ struct RenderParams {
     unsigned long long *counters;   // [0] next unit, [1] rays, [2] node visits, [3] tri tests, [4] hits shaded
     int32_t smem_nodes;             // nodes staged in shared memory (0 = none)
     int32_t block_stream_skip;      // per-block seeding served by skip-ahead (fixed draws per sample)
-    int32_t tail_lanes;             // a wave's walk is suspended once <= tail_lanes lanes are still walking (0 = never)
+    int32_t tail_lanes;             // wavefront engine: a walk is suspended once <= tail_lanes lanes are still walking (0 = never)
     float light_pos[3], light_energy[3];   // point light of the `simple` integrator (appended: older fields keep their offsets)
-    // deferred-occlusion engine (nb_wavefront.cu; unused by the kernels of nb_api.cu)
-    float4 *occ_queue;              // 4 x float4 per queued occlusion ray (OccRay)
-    uint32_t occ_capacity;          // rays the queue holds
-    int32_t slot_base;              // first owned-tile slot of this slice
     // wavefront engine (nb_wave.cu / nb_wave.cuh; unused by the other kernels)
+    float4 *occ_queue;              // occlusion queue: 3 x float4 per ray (origin | mint, direction | maxt, radiance | slot)
+    uint32_t occ_capacity;          // rays the queue holds (= wf_pool)
+    int32_t reserved0;
     float4 *wf_cols;                // path pool, structure of arrays: kWfCols columns of wf_pool float4 each
     uint32_t *wf_ext;               // queue of pool slots whose extension ray waits to be traced
     uint32_t *wf_ctr;               // engine counters (nb_wave.cuh: WF_*)
@@ -137,15 +130,6 @@ __device__ __forceinline__ void trav_begin(const Ray &r, Trav &t) {
     t.oodx = r.ox * t.idx; t.oody = r.oy * t.idy; t.oodz = r.oz * t.idz;
     t.hprim = 0xffffffffu; t.hu = 0.f; t.hv = 0.f;
     t.node = 0; t.sp = 0;
-}
-
-#ifndef NB_LDG256
-#define NB_LDG256 0
-#endif
-// 32 bytes (two float4) through the read-only path with ONE instruction; p must be 32-byte aligned
-__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 
 template <bool TMA_TOP>
@@ -209,22 +193,10 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
     while (node != kDone || parked != 0) {
         // ---- inner nodes
         while (node >= 0 && node != kDone) {
-#if NB_LDG256
-            // sm_100a has 256-bit global loads (SASS LDG.E.ENL2.256): a 64 B node is two load instructions instead of
-            // four -- half the L1 wavefronts of a lane-divergent node fetch, which is what bounds the walk
-            float4 n0, n1, n2, n3;
-            if (TMA_TOP && node < smem_nodes) {
-                n0 = snodes[node * 4 + 0]; n1 = snodes[node * 4 + 1]; n2 = snodes[node * 4 + 2]; n3 = snodes[node * 4 + 3];
-            } else {
-                ldg256(sc.nodes + (size_t) node * 4, n0, n1);
-                ldg256(sc.nodes + (size_t) node * 4 + 2, n2, n3);
-            }
-#else
             const float4 n0 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 0);
             const float4 n1 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 1);
             const float4 n2 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 2);
             const float4 n3 = ld_node<TMA_TOP>(sc, snodes, smem_nodes, node, 3);
-#endif
             if (COUNT) n_nodes++;
             // slab tests (explicit fma: may only cull; boxes are padded by the builder)
             float c0lox = __fmaf_rn(n0.x, t.idx, -t.oodx), c0hix = __fmaf_rn(n0.y, t.idx, -t.oodx);
@@ -276,10 +248,9 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
         if (leaf_test<COUNT>(sc, node, r, t, any_hit, n_tris)) break;
         node = sp ? stack[--sp] : kDone;
 #endif
-#if NB_TAIL_CUT || NB_DEFER_SHADOW
-        // ---- tail cut (experimental): when only a few lanes of the warp are still walking, they
-        // keep their (node, stack) and the warp goes on to shade / refill the finished lanes; the walk resumes in the next
-        // wave.  Checked at the END of an iteration so that every call makes progress (a check on entry livelocks as soon
+#if NB_WAVEFRONT
+        // ---- suspension (wavefront engine, nb_wave.cuh): when only a few lanes of the warp are still walking, they keep
+        // their (node, stack) and the warp goes on to retire / refill the finished lanes; the walk resumes afterwards.  Checked at the END of an iteration so that every call makes progress (a check on entry livelocks as soon
         // as a wave starts with <= tail lanes).
         if (tail > 0 && (node != kDone || parked != 0) && __popc(__activemask()) <= tail) {
             if (parked != 0) { if (node != kDone) stack[sp++] = node; node = parked; }
@@ -291,7 +262,7 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
     if (suspended) { t.node = node; t.sp = sp; } else { t.node = kDone; t.sp = 0; }
 }
 
-// Resumable walk for the render kernel: tr.node == kDone on entry means a fresh ray; otherwise (node, sp, stack) and the
+// Resumable walk (wavefront engine): tr.node == kDone on entry means a fresh ray; otherwise (node, sp, stack) and the
 // closest hit so far continue from where a tail cut suspended them.  The slab-test reciprocals are recomputed per call
 // so that only (node, sp, hit) stay live across the shading phase.
 template <bool COUNT, bool TMA_TOP>
@@ -419,7 +390,66 @@ __device__ __forceinline__ void splat(const RenderParams &P, int tile_slot, int 
     }
 }
 
-#if NB_DEFER_SHADOW == 2
+#ifndef NB_SPLAT_TILE
+#define NB_SPLAT_TILE 0      // A/B: per-warp shared-memory film tile, see splat_tile()
+#endif
+#if NB_SPLAT_TILE
+// Film-splat pre-reduction: a warp works through one work unit (an 8x4 pixel patch x a chunk of samples) at a time, and every
+// sample of that patch splats into the same (8+4) x (4+4) pixels.  The warp therefore keeps that rectangle in shared memory
+// (96 x float4 = 1.5 KB per warp), adds the samples of its CURRENT patch there (shared-memory float atomics: lanes collide),
+// and writes it out with one 128-bit RED per touched pixel when it moves on -- 96 global REDs per unit instead of 16 per
+// sample.  Paths that finish after their warp has moved to another patch, and filters with a border other than 2, take the
+// global path of splat().
+constexpr int kTileW = 12, kTileH = 8;
+struct WarpTile { int slot, px0, py0; bool valid; };      // warp-uniform: owned-tile slot and pixel origin of the patch
+
+__device__ __forceinline__ void tile_flush(const RenderParams &P, float4 *wt, WarpTile &T, unsigned lane) {
+    if (T.valid) {
+        const int tile_id = P.tile_rank + T.slot * P.tile_nranks;
+        const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+        float4 *blk = P.blocks + (size_t) T.slot * P.block_edge * P.block_edge;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int i = (int) lane + 32 * k;
+            const float4 v = wt[i];
+            if (v.w != 0.f || v.x != 0.f || v.y != 0.f || v.z != 0.f) {
+                // tile pixel (i % 12, i / 12) is block pixel (patch origin - tile origin + i) : the block's border equals the tile's margin
+                const int bx = T.px0 - tox + i % kTileW, by = T.py0 - toy + i / kTileW;
+                atomicAdd(&blk[by * P.block_edge + bx], v);
+                wt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// true if the sample was added to the warp's tile
+__device__ __forceinline__ bool splat_tile(const RenderParams &P, float4 *wt, const WarpTile &T, int tile_slot, int tsx, int tsy,
+                                           float sx, float sy, V3 value) {
+    const int px = (int) sx, py = (int) sy;
+    if (!T.valid || P.border != 2 || tile_slot != T.slot || px < T.px0 || px >= T.px0 + 8 || py < T.py0 || py >= T.py0 + 4) return false;
+    if (value.x < 0 || !isfinite(value.x) || value.y < 0 || !isfinite(value.y) || value.z < 0 || !isfinite(value.z)) return true;
+    const int tile_id = P.tile_rank + tile_slot * P.tile_nranks;
+    const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+    const float posx = sx - 0.5f - (float) (tox - 2), posy = sy - 0.5f - (float) (toy - 2);       // block coordinates, as in splat()
+    int x0 = (int) ceilf(posx - P.fradius), y0 = (int) ceilf(posy - P.fradius);
+    int x1 = (int) floorf(posx + P.fradius), y1 = (int) floorf(posy + P.fradius);
+    x0 = max(x0, 0); y0 = max(y0, 0);
+    x1 = min(x1, tsx + 3); y1 = min(y1, tsy + 3);
+    const int ox = T.px0 - tox, oy = T.py0 - toy;                                                  // block coordinates of tile pixel (0, 0)
+    for (int y = y0; y <= y1; ++y) {
+        const float wy = P.ftable[(int) (fabsf((float) y - posy) * P.lookup)];
+        for (int x = x0; x <= x1; ++x) {
+            const float wx = P.ftable[(int) (fabsf((float) x - posx) * P.lookup)];
+            float *t = reinterpret_cast<float *>(&wt[(y - oy) * kTileW + (x - ox)]);
+            atomicAdd(t + 0, value.x * wx * wy); atomicAdd(t + 1, value.y * wx * wy); atomicAdd(t + 2, value.z * wx * wy); atomicAdd(t + 3, 1.0f * wx * wy);
+        }
+    }
+    return true;
+}
+#endif
+
+#if NB_WAVEFRONT
 // Wavefront engine: one thread per pool slot (nb_wave.cuh: wf_logic_kernel).  An occlusion ray goes to the shadow queue with
 // the radiance it would add to the path and the slot it belongs to; wf_trace_kernel adds it to the slot's L if unoccluded.
 // A path emits at most one such ray per iteration, so the queue (one entry per slot) cannot overflow.
@@ -435,49 +465,6 @@ __device__ __forceinline__ bool occ_push(const RenderParams &P, const Ray &r, V3
     q[0] = make_float4(r.ox, r.oy, r.oz, r.mint);
     q[1] = make_float4(r.dx, r.dy, r.dz, r.maxt);
     q[2] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(blockIdx.x * blockDim.x + threadIdx.x));
-    return true;
-}
-#elif NB_DEFER_SHADOW
-// The filter is linear, so a sample's film contribution may be splatted in pieces: the path's own radiance with the
-// filter weight (splat above), and each unoccluded next-event / ambient-occlusion term later with weight 0.
-__device__ __forceinline__ void splat_contrib(const RenderParams &P, int tile_slot, float sx, float sy, V3 value) {
-    if (value.x < 0 || !isfinite(value.x) || value.y < 0 || !isfinite(value.y) || value.z < 0 || !isfinite(value.z)) return;
-    const int tile_id = P.tile_rank + tile_slot * P.tile_nranks;
-    const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
-    const int tsx = min(32, P.W - tox), tsy = min(32, P.H - toy);
-    const int bd = P.border;
-    const float posx = sx - 0.5f - (float) (tox - bd), posy = sy - 0.5f - (float) (toy - bd);
-    int x0 = (int) ceilf(posx - P.fradius), y0 = (int) ceilf(posy - P.fradius);
-    int x1 = (int) floorf(posx + P.fradius), y1 = (int) floorf(posy + P.fradius);
-    x0 = max(x0, 0); y0 = max(y0, 0);
-    x1 = min(x1, tsx + 2 * bd - 1); y1 = min(y1, tsy + 2 * bd - 1);
-    float4 *blk = P.blocks + (size_t) tile_slot * P.block_edge * P.block_edge;
-    for (int y = y0; y <= y1; ++y) {
-        const float wy = P.ftable[(int) (fabsf((float) y - posy) * P.lookup)];
-        for (int x = x0; x <= x1; ++x) {
-            const float wx = P.ftable[(int) (fabsf((float) x - posx) * P.lookup)];
-            atomicAdd(&blk[y * P.block_edge + x], make_float4(value.x * wx * wy, value.y * wx * wy, value.z * wx * wy, 0.0f));
-        }
-    }
-}
-
-// Queue entry of one occlusion ray: [o.xyz, mint] [d.xyz, maxt] [contribution rgb, sx] [sy, tile slot, -, -]
-// Appends with one atomic per converged group of lanes; returns false when the queue is full (the caller then traces
-// the ray itself, exactly as the fused kernel does).
-__device__ __forceinline__ bool occ_push(const RenderParams &P, const Ray &r, V3 contrib, float sx, float sy, int tile_slot) {
-    const unsigned mask = __activemask();
-    const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs(mask) - 1;
-    unsigned long long base = 0;
-    if ((int) lane == leader) base = atomicAdd(&P.counters[7], (unsigned long long) __popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    const unsigned long long idx = base + (unsigned long long) __popc(mask & ((1u << lane) - 1u));
-    if (idx >= (unsigned long long) P.occ_capacity) return false;
-    float4 *q = P.occ_queue + idx * 4ull;
-    q[0] = make_float4(r.ox, r.oy, r.oz, r.mint);
-    q[1] = make_float4(r.dx, r.dy, r.dz, r.maxt);
-    q[2] = make_float4(contrib.x, contrib.y, contrib.z, sx);
-    q[3] = make_float4(sy, __int_as_float(tile_slot), 0.f, 0.f);
     return true;
 }
 #endif
@@ -529,7 +516,7 @@ struct Path {
     unsigned char tsx, tsy;  // tile size
     unsigned char stage;
     bool prev_specular, has_next;
-#if NB_DEFER_SHADOW
+#if NB_WAVEFRONT
     unsigned deferred;       // occlusion rays this lane handed to the queue (they count as traced rays)
 #endif
 };
@@ -564,7 +551,7 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
         const V3 w = to_world(its.sh, square_to_cosine_hemisphere(x, y));
         ray.ox = its.p.x; ray.oy = its.p.y; ray.oz = its.p.z; ray.dx = w.x; ray.dy = w.y; ray.dz = w.z;
         ray.mint = NB_EPSILON; ray.maxt = NB_INF;
-#if NB_DEFER_SHADOW
+#if NB_WAVEFRONT
         if (occ_push(P, ray, mk(1, 1, 1), ps.sx, ps.sy, ps.tile_slot)) { ps.deferred++; return true; }   // L stays 0; visibility arrives through the queue
 #endif
         ps.stage = ST_SHADOW_AO;
@@ -582,7 +569,7 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
         ps.has_next = false;
         ray.ox = its.p.x; ray.oy = its.p.y; ray.oz = its.p.z; ray.dx = wo_w.x; ray.dy = wo_w.y; ray.dz = wo_w.z;
         ray.mint = NB_EPSILON; ray.maxt = dist - NB_EPSILON;
-#if NB_DEFER_SHADOW
+#if NB_WAVEFRONT
         if (occ_push(P, ray, ps.contrib, ps.sx, ps.sy, ps.tile_slot)) { ps.deferred++; return true; }
 #endif
         ps.stage = ST_SHADOW;                           // resolved by the ST_SHADOW branch above: L += contrib if unoccluded
@@ -673,7 +660,7 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
             ps.has_next = ps.depth < P.max_depth;
         }
     }
-#if NB_DEFER_SHADOW
+#if NB_WAVEFRONT
     // the shadow ray goes to the queue with its contribution; the path carries on with its extension ray at once
     if (want_shadow && occ_push(P, sray, ps.contrib, ps.sx, ps.sy, ps.tile_slot)) { ps.deferred++; want_shadow = false; }
 #endif
@@ -730,6 +717,25 @@ __device__ __forceinline__ void tma_stage_nodes(float4 *snodes, const float4 *gn
     }
 }
 
+// ------------------------------------------------------------------ L2 warm-up of the scene arrays
+// A frame starts with a cold L2 (another frame's blocks, the film, or the bench's flush went through it), and a walk that
+// demand-misses its first nodes to HBM pays the DRAM latency once per level.  One bulk prefetch instruction per 4 KB chunk
+// (cp.async.bulk.prefetch.L2, Hopper+) pulls the node and triangle arrays into L2 at full HBM speed -- 57 MB in ~10 us --
+// while the render kernel is being launched behind it.  Matters most when the frame is short (8 GPUs: 1.3 ms per frame).
+__global__ void l2_prefetch_kernel(const char *a, unsigned long long a_bytes, const char *b, unsigned long long b_bytes) {
+    constexpr unsigned long long kChunk = 4096ull;
+    const unsigned long long na = (a_bytes + kChunk - 1) / kChunk, nb_ = (b_bytes + kChunk - 1) / kChunk;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < na + nb_;
+         i += (unsigned long long) gridDim.x * blockDim.x) {
+        const bool first = i < na;
+        const unsigned long long off = (first ? i : i - na) * kChunk;
+        const unsigned long long total = first ? a_bytes : b_bytes;
+        const char *p = (first ? a : b) + off;
+        const unsigned bytes = (unsigned) ((total - off < kChunk ? total - off : kChunk) & ~15ull);    // multiple of 16 B
+        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ the fused persistent kernel (K1..K5)
 template <int INTEG, bool COUNT, bool TMA_TOP>
 __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCKS : NB_MIN_BLOCKS_PATH) render_kernel(const __grid_constant__ RenderParams P) {
@@ -741,14 +747,15 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-#if NB_TAIL_CUT
-    int stack[kStack + 1];        // per-lane traversal stack (local memory); survives a tail cut (+1: a parked leaf is pushed back)
+#if NB_SPLAT_TILE
+    __shared__ float4 wtiles[4][kTileW * kTileH];
+    float4 *wt = wtiles[threadIdx.x >> 5];
+    for (int k = 0; k < 3; ++k) wt[lane + 32 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    WarpTile WT; WT.valid = false; WT.slot = 0; WT.px0 = 0; WT.py0 = 0;
 #endif
     Path ps; Ray ray; Trav tr;
     ps.stage = ST_IDLE; tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu;
-#if NB_DEFER_SHADOW
-    ps.deferred = 0;
-#endif
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
     unsigned wave_nodes = 0; unsigned long long wave_max_sum = 0, n_waves = 0;
 
@@ -757,26 +764,15 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
 
-#if NB_TAIL_CUT || NB_DEFER_SHADOW
-    const long long wd_t0 = clock64();          // experimental engines: a bug must fail (counters[6] bit 63), never hang the GPU
-#endif
     for (;;) {
-#if NB_TAIL_CUT || NB_DEFER_SHADOW
-        if (__any_sync(0xffffffffu, clock64() - wd_t0 > NB_WATCHDOG_CYCLES)) { if (lane == 0) atomicOr(&P.counters[6], 1ull << 63); break; }
-#endif
         // ---- shading phase (lock step: every lane's ray is finished here)
-        if (ps.stage != ST_IDLE && traced && (!NB_TAIL_CUT || tr.node == kDone)) {
+        if (ps.stage != ST_IDLE && traced) {
             const bool finished = shade<INTEG>(P, ps, ray, tr, n_hits);
             if (finished) {
-#if NB_COMPACT_PATH
-                {   // tile geometry re-derived from the slot instead of carried per lane through the walk
-                    const int tile_id = P.tile_rank + ps.tile_slot * P.tile_nranks;
-                    const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
-                    splat(P, ps.tile_slot, tox, toy, min(32, P.W - tox), min(32, P.H - toy), ps.sx, ps.sy, ps.L);
-                }
-#else
-                splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
+#if NB_SPLAT_TILE
+                if (!splat_tile(P, wt, WT, ps.tile_slot, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L))
 #endif
+                splat(P, ps.tile_slot, ps.tox, ps.toy, ps.tsx, ps.tsy, ps.sx, ps.sy, ps.L);
                 ps.stage = ST_IDLE;
             } else {
                 n_rays++;
@@ -796,14 +792,18 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
                 const uint32_t rest = (uint32_t) (u / 32ULL);
                 const uint32_t chunk_id = rest % P.nchunks;
                 u_tile_slot = (int) (rest / P.nchunks);
-#if NB_DEFER_SHADOW
-                u_tile_slot += P.slot_base;               // this launch renders one slice of the owned tiles
-#endif
                 const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;
                 const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
                 u_tox = bx * 32; u_toy = by * 32;
                 u_tsx = min(32, P.W - u_tox); u_tsy = min(32, P.H - u_toy);
                 u_px0 = u_tox + (int) (patch & 3u) * 8; u_py0 = u_toy + (int) (patch >> 2) * 4;
+#if NB_SPLAT_TILE
+                if (!WT.valid || WT.slot != u_tile_slot || WT.px0 != u_px0 || WT.py0 != u_py0) {   // another patch (a new chunk of the same patch keeps the tile)
+                    __syncwarp();
+                    tile_flush(P, wt, WT, lane);
+                    WT.valid = true; WT.slot = u_tile_slot; WT.px0 = u_px0; WT.py0 = u_py0;
+                }
+#endif
                 const int lx = u_px0 + (int) (lane & 7u), ly = u_py0 + (int) (lane >> 3);
                 valid_mask = __ballot_sync(0xffffffffu, lx < P.W && ly < P.H);
                 n_valid = __popc(valid_mask);
@@ -819,10 +819,8 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
                 const uint32_t pix_slot = item % n_valid, s = sample_base + item / n_valid;
                 const int pl = __fns(valid_mask, 0, pix_slot + 1);      // lane index of the pix_slot-th valid pixel
                 ps.tile_slot = u_tile_slot;
-#if !NB_COMPACT_PATH
                 ps.tox = (short) u_tox; ps.toy = (short) u_toy;
                 ps.tsx = (unsigned char) u_tsx; ps.tsy = (unsigned char) u_tsy;
-#endif
                 begin_path(P, ps, ray, u_px0 + (pl & 7), u_py0 + (pl >> 3), s);
                 n_rays++;
                 need = false;
@@ -837,29 +835,14 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
         // (all NEE-resolve or all hit-shade) instead of a 50/50 mix, and any-hit waves are not held up by closest-hit.
         traced = (ps.stage != ST_IDLE);
         if (NB_PHASED_WAVES && (INTEG >= 2 || (NB_PHASED_AO && INTEG == 1))) {
-#if NB_TAIL_CUT
-            // suspended walks resume in every wave and do not vote on its kind (else a straggling shadow ray would
-            // hold the freshly regenerated camera rays back, wave after wave)
-            const bool carry = ps.stage != ST_IDLE && tr.node != kDone;
-            const bool any_shadow = __ballot_sync(0xffffffffu, !carry && ps.stage >= ST_SHADOW) != 0u;
-            traced = carry || (any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND));
-#else
             const bool any_shadow = __ballot_sync(0xffffffffu, ps.stage >= ST_SHADOW) != 0u;
             traced = (any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND));
-#endif
         }
         if (traced) {
-#if NB_TAIL_CUT
-            unsigned nn = 0, nt = 0;
-            walk_wave<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray, tr, stack, ps.stage != ST_EXTEND,
-                                      exhausted ? 0 : P.tail_lanes, nn, nt);
-            if (COUNT) { n_nodes += nn; n_tris += nt; wave_nodes = nn; }
-#else
             const WalkResult w = walk<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray.ox, ray.oy, ray.oz, ray.mint,
                                                       ray.dx, ray.dy, ray.dz, ray.maxt, ps.stage != ST_EXTEND);
             ray.maxt = w.t; tr.hu = w.u; tr.hv = w.v; tr.hprim = w.prim;
             if (COUNT) { n_nodes += w.n_nodes; n_tris += w.n_tris; wave_nodes = w.n_nodes; }
-#endif
         }
         if (COUNT) {
             // lock-step diagnostics: per wave, the longest walk (what the warp pays) vs the sum over lanes (what it needs)
@@ -870,10 +853,11 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
         }
     }
 
-    // counters: warp-reduce then one atomic per warp
-#if NB_DEFER_SHADOW
-    n_rays += ps.deferred;
+#if NB_SPLAT_TILE
+    __syncwarp();
+    tile_flush(P, wt, WT, lane);
 #endif
+    // counters: warp-reduce then one atomic per warp
     unsigned long long v1 = n_rays, v2 = n_nodes, v3 = n_tris, v4 = n_hits;
     for (int o = 16; o > 0; o >>= 1) {
         v1 += __shfl_down_sync(0xffffffffu, v1, o); v2 += __shfl_down_sync(0xffffffffu, v2, o);
@@ -946,58 +930,6 @@ __global__ void __launch_bounds__(128) li_samples_kernel(const __grid_constant__
     atomicAdd(&P.counters[4], (unsigned long long) n_hits);
 }
 
-#if NB_DEFER_SHADOW == 1
-// ------------------------------------------------------------------ occlusion kernel of the deferred engine
-// Traces the queued occlusion rays (any hit) and splats the contribution of the unoccluded ones.  Persistent warps with
-// dynamic fetch: a lane keeps its walk (node, stack) across refills; the warp leaves the walk as soon as at most
-// tail_lanes lanes are still walking, lets the finished lanes splat and take new rays from the queue (one atomic per
-// refill), and resumes.  Occlusion rays are incoherent and of very uneven length, which is what makes them expensive in
-// the lock-step kernel; here the lanes stay busy.
-__global__ void __launch_bounds__(128, NB_MIN_BLOCKS) occlusion_kernel(const __grid_constant__ RenderParams P) {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int stack[kStack + 1];
-    Ray ray; Trav tr;
-    tr.node = kDone; tr.sp = 0; tr.hprim = 0xffffffffu; tr.hu = 0.f; tr.hv = 0.f;
-    V3 contrib = mk(0, 0, 0); float sx = 0.f, sy = 0.f; int tile_slot = 0;
-    bool active = false, exhausted = false;
-    unsigned long long n_in = P.counters[7];
-    if (n_in > (unsigned long long) P.occ_capacity) n_in = P.occ_capacity;
-    const long long wd_t0 = clock64();
-    for (;;) {
-        if (__any_sync(0xffffffffu, clock64() - wd_t0 > NB_WATCHDOG_CYCLES)) { if (lane == 0) atomicOr(&P.counters[6], 1ull << 63); break; }
-        // ---- refill (all 32 lanes are converged here)
-        const unsigned idle_mask = __ballot_sync(0xffffffffu, !active);
-        if (idle_mask != 0u && !exhausted) {
-            const unsigned n_idle = __popc(idle_mask);
-            unsigned long long start = 0;
-            if (lane == 0) start = atomicAdd(&P.counters[0], (unsigned long long) n_idle);
-            start = __shfl_sync(0xffffffffu, start, 0);
-            const unsigned long long idx = start + (unsigned long long) __popc(idle_mask & lt_mask);
-            if (!active && idx < n_in) {
-                const float4 *q = P.occ_queue + idx * 4ull;
-                const float4 a = q[0], b = q[1], c = q[2], d = q[3];
-                ray.ox = a.x; ray.oy = a.y; ray.oz = a.z; ray.mint = a.w;
-                ray.dx = b.x; ray.dy = b.y; ray.dz = b.z; ray.maxt = b.w;
-                contrib = mk(c.x, c.y, c.z); sx = c.w; sy = d.x; tile_slot = __float_as_int(d.y);
-                tr.node = kDone;                           // fresh ray for walk_wave
-                active = true;
-            }
-            if (start + (unsigned long long) n_idle >= n_in) exhausted = true;
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u) break;
-        // ---- walk until at most tail_lanes lanes are left (to completion once the queue is drained)
-        if (active) {
-            unsigned nn = 0, nt = 0;
-            walk_wave<false, false>(P.sc.nodes, P.sc.tris, nullptr, 0, ray, tr, stack, true, exhausted ? 0 : P.tail_lanes, nn, nt);
-            if (tr.node == kDone) {
-                if (tr.hprim == 0xffffffffu) splat_contrib(P, tile_slot, sx, sy, contrib);
-                active = false;
-            }
-        }
-    }
-}
-#endif
 
 // ------------------------------------------------------------------ K6: merge finished blocks into the full film (ref: src/block.cpp:93-102)
 __global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank, int nranks, int ntx, int W, int H,

@@ -1,11 +1,11 @@
 // nb_wave.cu -- launchers of the wavefront engine (nb_wave.cuh; nb_set_option(ctx, "engine", 2)).
 //
-// Its own translation unit for the same two reasons as nb_wavefront.cu: the kernels of nb_api.cu must not change by an
-// instruction when this engine is edited, and nb_device.cuh defines non-inline device functions whose host stubs would collide
-// at link time -- hence the private namespace name.  shade<INTEG>() is compiled here with NB_DEFER_SHADOW = 2: occlusion rays
-// go to the engine's shadow queue (nb_kernels.cuh: occ_push) instead of being traced by the thread that generated them.
+// Its own translation unit for two reasons: the kernels of nb_api.cu must not change by an instruction when this engine is
+// edited, and nb_device.cuh defines non-inline device functions whose host stubs would collide at link time -- hence the
+// private namespace name.  shade<INTEG>() is compiled here with NB_WAVEFRONT = 1: occlusion rays go to the engine's shadow
+// queue (nb_kernels.cuh: occ_push) instead of being traced by the thread that generated them.
 #define nb nb_wv
-#define NB_DEFER_SHADOW 2
+#define NB_WAVEFRONT 1
 #include "nb_wave.cuh"
 #include <cstring>
 
