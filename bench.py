@@ -146,12 +146,18 @@ def ncu_capture(workload):
         return {}
 
 
+def node_bytes():
+    from nori_b200 import abi
+    return int(abi.lib().nb_node_bytes())
+
+
 def algorithmic_bytes(node_visits, tri_tests, hits_shaded, scene, has_uv):
-    """64 B per BVH node visit + 48 B per triangle test + 36 B of normals per shaded closest hit
-    (+24 B UVs when present) + one film write; rays are generated and consumed in registers (0 B)."""
+    """the bytes of one node per BVH node visit (64 B for the binary node the survey assumed, 80 B for the
+    8-wide compressed node this build walks -- nb_node_bytes()) + 48 B per triangle test + 36 B of normals per shaded
+    closest hit (+24 B UVs when present) + one film write; rays are generated and consumed in registers (0 B)."""
     b = scene.border
     film = (scene.camera.width + 2 * b) * (scene.camera.height + 2 * b) * 16
-    return 64 * node_visits + 48 * tri_tests + (36 + (24 if has_uv else 0)) * hits_shaded + film
+    return node_bytes() * node_visits + 48 * tri_tests + (36 + (24 if has_uv else 0)) * hits_shaded + film
 
 
 def config_dict(name, scene, n_tris):
@@ -343,7 +349,7 @@ def roofline_record(name, scene, counts, kern_ms, world, has_uv, info):
            "frac_is": "EFFECTIVE (cache-served): algorithmic bytes of SURVEY 8d / kernel time; the scene is L2-resident, see `secondary` for the real bound",
            "traffic": cap.get("bytes") if world == 1 else None, "peak_source": peak_src,
            "kernel": "render_kernel<%s>" % INT_NAMES[scene.integrator], "kernel_ms": kern_ms,
-           "algorithmic_bytes_per_launch": alg / world, "node_visits": nodes, "tri_tests": tris, "hits_shaded": hits,
+           "algorithmic_bytes_per_launch": alg / world, "node_visits": nodes, "node_bytes": node_bytes(), "tri_tests": tris, "hits_shaded": hits,
            "scene_mb": info["bytes"] / 1e6}
     if cap:
         sec = {k: cap[k] for k in ("issue_active_pct", "lanes_per_inst", "lsu_wavefronts_pct_of_peak", "l1_hit_pct", "l2_hit_pct",

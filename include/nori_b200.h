@@ -85,6 +85,9 @@ nb_ctx *nb_create(int device);
 void    nb_destroy(nb_ctx *);
 const char *nb_last_error(void);
 int     nb_abi_version(void);
+/* Bytes one node visit of the walk fetches: 64 (binary node: two child boxes + two references) or 80 (8-wide compressed node,
+ * nori_b200/csrc/nb_wide.h) -- the per-visit figure of the algorithmic-bytes accounting (bench.py). */
+int     nb_node_bytes(void);
 
 /* ---- N GPUs behind the same calls (replaces the TBB tile loop + merge for N devices, ref: src/main.cpp:85-113,
  * src/block.cpp:93-102).  nb_create_multi returns ONE context (on devices[0]) that owns a context per further device
@@ -214,6 +217,17 @@ int nb_film_to_rgb(nb_ctx *, const float *film_host, float *rgb_host);
  * equal the host loop's (both sides evaluate x^(1/2.4) with the same polynomials). */
 int nb_last_film_to_srgb8(nb_ctx *, uint8_t *rgb8_host);
 
+/* Progressive frames -- the role of NoriScreen, which redraws from the shared ImageBlock while tiles are still being rendered
+ * (ref: src/gui.cpp:120-138): the frame is rendered in passes of n sample streams per pixel; the accumulators stay on the
+ * device, and after any pass nb_render_preview merges them into a film (film_host, nullable: (H+2b) x (W+2b) x 4 floats)
+ * and/or the tonemapped 8-bit image (rgb8_host, nullable: W x H x 3).  The un-normalised film of k passes is exactly the
+ * film of the first k * n samples, so every preview is a valid image and the last one equals nb_render's (up to the order
+ * of the film atomics).  nb_render_pass stats accumulate over the passes.  Single-device contexts, NB_SEED_PER_SAMPLE. */
+int nb_render_begin(nb_ctx *);
+int nb_render_pass(nb_ctx *, uint32_t n_samples, nb_stats *stats /* nullable */);
+int nb_render_preview(nb_ctx *, float *film_host, uint8_t *rgb8_host);
+int nb_render_end(nb_ctx *);
+
 /* Tuning knobs (optional; sane defaults): key/value, see DESIGN.md section 6.  Unknown key -> error. */
 int nb_set_option(nb_ctx *, const char *key, int64_t value);
 /* Raw device counters of the last call (diagnostics; meaningful with option "count" = 1): [1] rays, [2] node visits,
@@ -229,6 +243,15 @@ int nb_debug_build_bvh(const float *verts4, const uint32_t *faces4, uint32_t npr
  * nb_set_accel_cache.  info = { nodes, leaf triangles, top nodes, depth, hit (0/1) }. */
 int nb_debug_bvh_cache(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes, const char *path,
                        float *nodes_out, uint64_t nodes_cap, float *tris_out, uint64_t tris_cap, uint32_t info[5]);
+/* Host-only diagnostics of the 8-wide compressed hierarchy (nori_b200/csrc/nb_wide.h): binary SAH build (max_leaf 3) + collapse;
+ * nodes_out = 20 words per wide node, tris_out = 12 floats per triangle; info = { wide nodes, triangles, wide depth, binary
+ * nodes }.  nb_debug_wide_intersect walks it on the HOST with the kernels' own node step (rays: o, mint, d, maxt = 8 floats;
+ * hits4: t, u, v, triangle bits (NB_MISS = none); counts (nullable) = { node visits, triangle tests }): the CPU tests use it
+ * to check the builder and the walk's logic against the oracle's brute-force loop without a GPU. */
+int nb_debug_build_wide(const float *verts4, const uint32_t *faces4, uint32_t nprims, uint32_t *nodes_out, uint64_t nodes_cap,
+                        float *tris_out, uint64_t tris_cap, uint32_t info[4]);
+int nb_debug_wide_intersect(const uint32_t *nodes, uint32_t nnodes, const float *tris, const float *rays, uint64_t nrays,
+                            int any_hit, float *hits4, uint64_t counts[2]);
 /* Scene geometry summary after nb_build_accel. */
 int nb_scene_info(nb_ctx *, uint64_t *ntris, uint64_t *nnodes, uint64_t *scene_bytes, int *bvh_depth);
 

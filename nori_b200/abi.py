@@ -71,12 +71,15 @@ def lib():
         L.nb_destroy.argtypes = [vp]; L.nb_destroy.restype = None
         L.nb_last_error.restype = C.c_char_p
         L.nb_abi_version.restype = i
+        L.nb_node_bytes.restype = i
         L.nb_add_mesh.argtypes = [vp, vp, u32, vp, vp, vp, u32, C.POINTER(BsdfDesc), C.POINTER(EmitterDesc)]
         L.nb_clear_meshes.argtypes = [vp]
         L.nb_build_accel.argtypes = [vp]
         L.nb_upload_scene.argtypes = [vp]
         L.nb_set_accel_cache.argtypes = [vp, C.c_char_p]
         L.nb_accel_cache_hit.argtypes = [vp]
+        L.nb_debug_build_wide.argtypes = [vp, vp, u32, vp, u64, vp, u64, vp]
+        L.nb_debug_wide_intersect.argtypes = [vp, u32, vp, vp, u64, i, vp, vp]
         L.nb_debug_bvh_cache.argtypes = [vp, vp, u32, i, C.c_int64, C.c_char_p, vp, u64, vp, u64, vp]
         L.nb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i)]
         L.nb_set_camera.argtypes = [vp, vp, vp, i, i, f, f]
@@ -100,6 +103,10 @@ def lib():
         L.nb_intersect_full.argtypes = [vp, vp, u64, vp]
         L.nb_film_to_rgb.argtypes = [vp, vp, vp]
         L.nb_last_film_to_srgb8.argtypes = [vp, vp]
+        L.nb_render_begin.argtypes = [vp]
+        L.nb_render_pass.argtypes = [vp, u32, sp]
+        L.nb_render_preview.argtypes = [vp, vp, vp]
+        L.nb_render_end.argtypes = [vp]
         L.nb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         L.nb_debug_counters.argtypes = [vp, vp]
         L.nb_debug_build_bvh.argtypes = [vp, vp, u32, i, C.c_int64, vp, u64, vp, u64, vp]
@@ -132,6 +139,33 @@ def debug_build_bvh(V: np.ndarray, F: np.ndarray, max_leaf=3, bfs_nodes=2048):
     if rc:
         raise NoriError(f"nb_debug_build_bvh failed ({rc})")
     return nodes, tris, dict(nodes=int(info[0]), tris=int(info[1]), top_nodes=int(info[2]), depth=int(info[3]))
+
+
+def debug_build_wide(V: np.ndarray, F: np.ndarray):
+    """The 8-wide compressed hierarchy of the product (nb_wide.h), built without a GPU: (nodes [n,20] uint32, tris [m,12] float32, info)."""
+    L = lib()
+    v4 = np.zeros((V.shape[0], 4), dtype=np.float32); v4[:, :3] = V
+    f4 = np.zeros((F.shape[0], 4), dtype=np.uint32); f4[:, :3] = F
+    info = np.zeros(4, dtype=np.uint32)
+    rc = L.nb_debug_build_wide(_p(v4), _p(f4), F.shape[0], None, 0, None, 0, _p(info))
+    if rc:
+        raise NoriError(f"nb_debug_build_wide failed ({rc})")
+    nodes = np.zeros((int(info[0]), 20), dtype=np.uint32); tris = np.zeros((int(info[1]), 12), dtype=np.float32)
+    rc = L.nb_debug_build_wide(_p(v4), _p(f4), F.shape[0], _p(nodes), nodes.size, _p(tris), tris.size, _p(info))
+    if rc:
+        raise NoriError(f"nb_debug_build_wide failed ({rc})")
+    return nodes, tris, dict(nodes=int(info[0]), tris=int(info[1]), depth=int(info[2]), binary_nodes=int(info[3]))
+
+
+def debug_wide_intersect(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, any_hit=False):
+    """Host reference walk over a wide hierarchy with the kernels' node step: rays RAY_DTYPE -> (hits HIT_DTYPE-like t,u,v,prim; counts)."""
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    out = np.zeros((rays.shape[0], 4), dtype=np.float32)
+    counts = np.zeros(2, dtype=np.uint64)
+    rc = lib().nb_debug_wide_intersect(_p(nodes), nodes.shape[0], _p(tris), _p(rays), rays.shape[0], int(any_hit), _p(out), _p(counts))
+    if rc:
+        raise NoriError(f"nb_debug_wide_intersect failed ({rc})")
+    return out, counts
 
 
 def debug_bvh_cache(V: np.ndarray, F: np.ndarray, path: str, max_leaf=3, bfs_nodes=2048):
@@ -366,6 +400,24 @@ class Context:
         out = np.zeros((rays.shape[0], 16), dtype=np.float32)
         _check(lib().nb_intersect_full(self.h, _p(rays), rays.shape[0], _p(out)))
         return out
+
+    def render_progressive(self, samples_per_pass: int, want_rgb8: bool = False):
+        """Generator over the passes of a progressive frame (nb_render_begin / _pass / _preview / _end): yields
+        (samples_done, film, rgb8 or None, stats) after every pass; the last film is the full frame."""
+        _check(lib().nb_render_begin(self.h))
+        try:
+            done, spp = 0, int(self.scene.spp)
+            while done < spp:
+                n = min(int(samples_per_pass), spp - done)
+                st = Stats()
+                _check(lib().nb_render_pass(self.h, n, C.byref(st)))
+                done += n
+                film = np.zeros(self.scene.film_shape, dtype=np.float32)
+                rgb8 = np.zeros((self.scene.camera.height, self.scene.camera.width, 3), dtype=np.uint8) if want_rgb8 else None
+                _check(lib().nb_render_preview(self.h, _p(film), _p(rgb8)))
+                yield done, film, rgb8, st
+        finally:
+            lib().nb_render_end(self.h)
 
     def last_film_to_srgb8(self):
         """nb_last_film_to_srgb8: the last nb_render's film, normalised + sRGB-tonemapped + quantised on the device: (H, W, 3) uint8."""

@@ -46,8 +46,8 @@ def build_cuda(force=False, variant="", extra_flags=()):
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB, exist_ok=True)
     target = os.path.join(LIB, f"libnori_b200{variant}.so")
-    srcs = [os.path.join(CSRC, f) for f in ("nb_api.cu", "nb_aux.cu", "nb_wave.cu", "nb_bvh.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("nb_bvh.h", "nb_kernels.cuh", "nb_device.cuh", "nb_lbvh.cuh", "nb_ctx.h", "nb_multi.inl", "nb_wave.cuh")
+    srcs = [os.path.join(CSRC, f) for f in ("nb_api.cu", "nb_aux.cu", "nb_wave.cu", "nb_bvh.cpp", "nb_wide.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("nb_bvh.h", "nb_kernels.cuh", "nb_device.cuh", "nb_lbvh.cuh", "nb_ctx.h", "nb_multi.inl", "nb_wave.cuh", "nb_wide.h")
                    if os.path.exists(os.path.join(CSRC, f))] + [os.path.join(os.path.dirname(HERE), "include", "nori_b200.h")]
     if force or _stale(target, deps):
         objdir = os.path.join(LIB, f"obj{variant}")

@@ -3,6 +3,7 @@
 // main.cpp -- `nori <scene.xml>` command line (ref: src/main.cpp:150-246).  --no-gui / --threads are accepted for
 // compatibility and ignored (there is no GUI and no TBB on this path); --device N selects the GPU, --gpus N
 // renders on N devices (tiles sharded tile_id % N, finished ImageBlocks gathered over NCCL, merged on the first device),
+// --preview K renders progressively (K samples per pass) and rewrites <scene>_preview.png after every pass,
 // --cache keeps the built BVH in <scene>.nbbvh and reloads it when the geometry is unchanged.
 #include <cstring>
 #include "nori/parser.h"
@@ -12,7 +13,7 @@ using namespace nori;
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N] [--gpus N] [--lbvh] [--cache]" << endl;
+        cerr << "Syntax: " << argv[0] << " <scene.xml> [--no-gui] [--threads N] [--device N] [--gpus N] [--lbvh] [--cache] [--preview SPP]" << endl;
         return -1;
     }
     std::string sceneName;
@@ -25,6 +26,9 @@ int main(int argc, char **argv) {
         } else if (token == "--no-gui") {
         } else if (token == "--lbvh") {
             opt.deviceBuilder = true;   // GPU-built hierarchy (fast build, slightly slower render)
+        } else if (token == "--preview") {
+            if (i + 1 >= argc || atoi(argv[i + 1]) < 1) { cerr << "\"--preview\" expects a positive sample count following it." << endl; return -1; }
+            opt.previewEvery = atoi(argv[++i]);   // progressive frame: <scene>_preview.png rewritten after every pass of that many samples
         } else if (token == "--cache") {
             opt.accelCache = "?";       // resolved below: <scene>.nbbvh next to the scene file
         } else if (token == "--gpus") {

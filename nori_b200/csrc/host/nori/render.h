@@ -17,6 +17,8 @@ struct RenderOptions {
     int tileRank = 0, tileRanks = 1;   // tile shard (multi-GPU: one process per GPU)
     bool quiet = false;
     bool deviceBuilder = false;        // build the hierarchy on the GPU (LBVH) instead of the host SAH builder
+    int previewEvery = 0;              // > 0: render progressively, that many samples per pass, and rewrite <scene>_preview.png after every pass
+    std::string previewName;           // file name stem of the preview image
     std::string accelCache;            // file caching the built hierarchy (nb_set_accel_cache); empty = build every time
 };
 

@@ -129,7 +129,24 @@ void renderScene(Scene *scene, ImageBlock &result, const RenderOptions &opt, nb_
     nb_ctx *ctx = createDeviceScene(scene, result, opt);
     nb_stats st; std::memset(&st, 0, sizeof st);
     result.clear();
-    int rc = nb_render(ctx, result.data(), &st);                  // replaces ref: src/main.cpp:64-119
+    int rc = 0;
+    const int spp = (int) scene->getSampler()->getSampleCount();
+    if (opt.previewEvery > 0 && opt.gpus <= 1 && opt.previewEvery < spp) {
+        // progressive frame: passes of previewEvery samples; after each one the device merges + tonemaps what it has and the
+        // host rewrites the preview image -- the job of NoriScreen's refresh (ref: src/gui.cpp:120-138) without a window
+        std::vector<uint8_t> p8((size_t) result.getSize().x() * result.getSize().y() * 3);
+        rc = nb_render_begin(ctx);
+        for (int done = 0; !rc && done < spp; ) {
+            const int n = std::min(opt.previewEvery, spp - done);
+            rc = nb_render_pass(ctx, (uint32_t) n, &st);
+            done += n;
+            if (!rc) rc = nb_render_preview(ctx, done >= spp ? result.data() : nullptr, p8.data());
+            if (!rc && !opt.previewName.empty()) Bitmap::savePNG8(opt.previewName, result.getSize().x(), result.getSize().y(), p8.data());
+        }
+        if (!rc) nb_render_end(ctx);
+    } else {
+        rc = nb_render(ctx, result.data(), &st);                  // replaces ref: src/main.cpp:64-119
+    }
     if (!rc && srgb8) {                                           // tonemap + 8-bit pack on the device (ref: src/common.cpp:166-180, src/bitmap.cpp:100-110)
         srgb8->resize((size_t) result.getSize().x() * result.getSize().y() * 3);
         rc = nb_last_film_to_srgb8(ctx, srgb8->data());
@@ -147,7 +164,9 @@ void render(Scene *scene, const std::string &filename, const RenderOptions &opt)
     nb_stats st;
     auto t0 = std::chrono::steady_clock::now();
     std::vector<uint8_t> srgb8;
-    renderScene(scene, result, opt, &st, &srgb8);
+    RenderOptions ropt = opt;
+    if (ropt.previewEvery > 0) { ropt.previewName = filename; size_t dot = ropt.previewName.find_last_of("."); if (dot != std::string::npos) ropt.previewName.erase(dot); ropt.previewName += "_preview"; }
+    renderScene(scene, result, ropt, &st, &srgb8);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (!opt.quiet)
         cout << "done. (took " << timeString(ms) << " incl. upload + BVH build; render kernel " << timeString(st.kernel_ms, true) << ", "

@@ -53,6 +53,60 @@ int fill_scene(nb_ctx *c, nb::SceneDev &sc) {
     return 0;
 }
 
+constexpr size_t kArenaAlign = 256, kArenaSlack = 64 * 256;      // slack: a group of up to 64 ranks pads the arena to N equal shards
+
+// offsets of the nine tables inside the arena, from their element counts (the same on every rank of a group)
+size_t arena_layout(const size_t counts[9], size_t offs[9]) {
+    const size_t elem[9] = { sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float2), sizeof(uint4), sizeof(nb::DevMesh), sizeof(float), sizeof(int32_t) };
+    size_t off = 0;
+    for (int i = 0; i < 9; ++i) { offs[i] = off; off += (counts[i] * elem[i] + kArenaAlign - 1) / kArenaAlign * kArenaAlign; }
+    return off;
+}
+
+void arena_counts(const nb_ctx *c, size_t counts[9]) {
+    const size_t n[9] = { c->nodes.n, c->tris.n, c->verts.n, c->normals.n, c->uvs.n, c->faces.n, c->dmeshes.n, c->cdf.n, c->emitters.n };
+    for (int i = 0; i < 9; ++i) counts[i] = n[i];
+}
+
+void arena_views(nb_ctx *c, const size_t counts[9], const size_t offs[9]) {
+    c->nodes.set_view(c->arena_d, c->arena_h, offs[0], counts[0]); c->tris.set_view(c->arena_d, c->arena_h, offs[1], counts[1]);
+    c->verts.set_view(c->arena_d, c->arena_h, offs[2], counts[2]); c->normals.set_view(c->arena_d, c->arena_h, offs[3], counts[3]);
+    c->uvs.set_view(c->arena_d, c->arena_h, offs[4], counts[4]); c->faces.set_view(c->arena_d, c->arena_h, offs[5], counts[5]);
+    c->dmeshes.set_view(c->arena_d, c->arena_h, offs[6], counts[6]); c->cdf.set_view(c->arena_d, c->arena_h, offs[7], counts[7]);
+    c->emitters.set_view(c->arena_d, c->arena_h, offs[8], counts[8]);
+}
+
+void arena_release(nb_ctx *c) {
+    c->nodes.release(); c->tris.release(); c->verts.release(); c->normals.release(); c->uvs.release(); c->faces.release();
+    c->dmeshes.release(); c->cdf.release(); c->emitters.release();
+    if (c->arena_d) cudaFree(c->arena_d);
+    if (c->arena_h) cudaFreeHost(c->arena_h);
+    c->arena_d = nullptr; c->arena_h = nullptr; c->arena_bytes = 0;
+}
+
+// Moves the nine separately allocated tables of a finished build (device data + pinned mirrors) into one arena.
+int arena_pack(nb_ctx *c) {
+    size_t counts[9], offs[9];
+    arena_counts(c, counts);
+    const size_t total = arena_layout(counts, offs);
+    char *ad = nullptr, *ah = nullptr;
+    CK(cudaMalloc(&ad, total + kArenaSlack));
+    if (cudaMallocHost(&ah, total + kArenaSlack) != cudaSuccess) { cudaFree(ad); return fail("cudaMallocHost(%zu) failed", total); }
+    memset(ah, 0, total + kArenaSlack);
+    cudaStream_t s = c->stream;
+    cudaError_t e = cudaMemsetAsync(ad, 0, total + kArenaSlack, s);
+#define PK(buf, i) do { if (e == cudaSuccess && c->buf.n) { e = cudaMemcpyAsync(ad + offs[i], c->buf.d, c->buf.bytes(), cudaMemcpyDeviceToDevice, s); \
+                        memcpy(ah + offs[i], c->buf.h, c->buf.bytes()); } } while (0)
+    PK(nodes, 0); PK(tris, 1); PK(verts, 2); PK(normals, 3); PK(uvs, 4); PK(faces, 5); PK(dmeshes, 6); PK(cdf, 7); PK(emitters, 8);
+#undef PK
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cudaFree(ad); cudaFreeHost(ah); return fail("arena_pack failed: %s", cudaGetErrorString(e)); }
+    arena_release(c);
+    c->arena_d = ad; c->arena_h = ah; c->arena_bytes = total;
+    arena_views(c, counts, offs);
+    return 0;
+}
+
 template <int INTEG>
 void launch_render(const nb::RenderParams &P, bool count, bool block_mode, int grid, size_t smem, cudaStream_t s) {
     if (block_mode) {
@@ -94,7 +148,8 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     P.nearClip = c->nearClip; P.farClip = c->farClip;
     memcpy(P.ftable, c->ftable, sizeof P.ftable);
     P.fradius = c->fradius; P.lookup = NB_FILTER_RESOLUTION / c->fradius; P.border = c->border;   // ref: src/block.cpp:20,27
-    P.spp = c->spp; P.seed_mode = c->seed_mode; P.seed = c->seed;
+    const uint32_t spp = c->prog_active ? c->prog_pass : c->spp;       // a progressive pass renders prog_pass sample streams from prog_done on
+    P.spp = spp; P.sample_offset = c->prog_active ? c->prog_done : 0u; P.seed_mode = c->seed_mode; P.seed = c->seed;
     P.integrator = c->integ.type; P.rr_start = c->integ.rr_start > 0 ? c->integ.rr_start : 3;
     P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
     P.tile_rank = c->tile_rank; P.tile_nranks = c->tile_nranks;
@@ -106,11 +161,11 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     int64_t chunk = c->opt_chunk;
     if (chunk <= 0) {
         const int64_t warps = (int64_t) c->sm_count * NB_MIN_BLOCKS * 4;
-        const int64_t units1 = (int64_t) P.n_my_tiles * 32 * c->spp;
+        const int64_t units1 = (int64_t) P.n_my_tiles * 32 * spp;
         chunk = std::max<int64_t>(1, std::min<int64_t>(8, units1 / (16 * warps)));
     }
-    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, c->spp));
-    P.nchunks = (c->spp + P.chunk - 1) / P.chunk;
+    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, spp));
+    P.nchunks = (spp + P.chunk - 1) / P.chunk;
     const unsigned long long units = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
     if (units > 0xffffffffULL) return fail("too many work units");
     P.n_units = (uint32_t) units;
@@ -149,7 +204,7 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
 
     CK(cudaEventRecord(c->ev[0], s));
     CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s));
-    if (blk_elems) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));
+    if (blk_elems && !c->prog_active) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));   // a progressive pass accumulates
     CK(cudaEventRecord(c->ev[1], s));
     // L2 warm-up (inside the timed region): only when the walk's arrays fit L2 with room to spare, and never for the
     // one-thread-per-block plumbing mode
@@ -181,7 +236,7 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
             int tile_id = c->tile_rank + k * c->tile_nranks, bx = tile_id % P.ntx, by = tile_id / P.ntx;
             ns += (unsigned long long) std::min(32, c->W - bx * 32) * std::min(32, c->H - by * 32);
         }
-        st->samples = ns * c->spp;
+        st->samples = ns * spp;
         st->launches = P.n_my_tiles > 0 ? 1 : 0;
     }
     return 0;
@@ -212,16 +267,17 @@ int render_blocks_wave(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *
     P.nearClip = c->nearClip; P.farClip = c->farClip;
     memcpy(P.ftable, c->ftable, sizeof P.ftable);
     P.fradius = c->fradius; P.lookup = NB_FILTER_RESOLUTION / c->fradius; P.border = c->border;
-    P.spp = c->spp; P.seed_mode = c->seed_mode; P.seed = c->seed;
+    const uint32_t spp = c->prog_active ? c->prog_pass : c->spp;       // a progressive pass renders prog_pass sample streams from prog_done on
+    P.spp = spp; P.sample_offset = c->prog_active ? c->prog_done : 0u; P.seed_mode = c->seed_mode; P.seed = c->seed;
     P.integrator = c->integ.type; P.rr_start = c->integ.rr_start > 0 ? c->integ.rr_start : 3;
     P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
     P.tile_rank = c->tile_rank; P.tile_nranks = c->tile_nranks;
     P.n_my_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, &P.ntx, &P.nty);
     P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
     if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
-    P.wf_chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(c->opt_chunk > 0 ? c->opt_chunk : 8, std::min<int64_t>(8, c->spp)));
+    P.wf_chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(c->opt_chunk > 0 ? c->opt_chunk : 8, std::min<int64_t>(8, spp)));
     P.chunk = P.wf_chunk;
-    P.nchunks = (c->spp + P.wf_chunk - 1) / P.wf_chunk;
+    P.nchunks = (spp + P.wf_chunk - 1) / P.wf_chunk;
     P.wf_total = (unsigned long long) P.n_my_tiles * 32ull * P.nchunks * 32ull * P.wf_chunk;
     // pool: as many slots as asked for, never more than there are samples, a multiple of 128
     unsigned long long pool = (unsigned long long) std::max<int64_t>(128, c->opt_wf_pool);
@@ -267,7 +323,7 @@ int render_blocks_wave(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *
     CK(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 8, s));
     CK(cudaMemsetAsync(c->wf_ctr, 0, sizeof(uint32_t) * 8, s));
     CK(cudaMemsetAsync(c->wf_cols + (size_t) 4 * pool, 0, sizeof(float4) * pool, s));      // column 4 holds the slot state: all empty
-    if (blk_elems) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));
+    if (blk_elems && !c->prog_active) CK(cudaMemsetAsync(blocks_out, 0, sizeof(float4) * blk_elems, s));   // a progressive pass accumulates
     CK(cudaEventRecord(c->ev[1], s));
     unsigned long long launches = 0;
     const int check = (int) std::max<int64_t>(1, c->opt_wf_check);
@@ -296,7 +352,7 @@ int render_blocks_wave(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *
             int tile_id = c->tile_rank + k * c->tile_nranks, bx = tile_id % P.ntx, by = tile_id / P.ntx;
             ns += (unsigned long long) std::min(32, c->W - bx * 32) * std::min(32, c->H - by * 32);
         }
-        st->samples = ns * c->spp;
+        st->samples = ns * spp;
         st->launches = launches;
     }
     return 0;
@@ -399,6 +455,7 @@ extern "C" {
 
 const char *nb_last_error(void) { return nbi::g_err.c_str(); }
 int nb_abi_version(void) { return NB_ABI_VERSION; }
+int nb_node_bytes(void) { return NB_WIDE ? 80 : 64; }
 
 nb_ctx *nb_create(int device) {
     int ndev = 0;
@@ -432,8 +489,8 @@ void nb_destroy(nb_ctx *c) {
     c->followers.clear();
     cudaSetDevice(c->device);
     nbm::release_group(c);
-    c->nodes.release(); c->tris.release(); c->verts.release(); c->normals.release(); c->uvs.release(); c->faces.release();
-    c->dmeshes.release(); c->cdf.release(); c->emitters.release();
+    arena_release(c);
+    if (c->shard_h) cudaFreeHost(c->shard_h);
     if (c->blocks) cudaFree(c->blocks);
     if (c->film) cudaFree(c->film);
     if (c->wf_cols) cudaFree(c->wf_cols);
@@ -482,12 +539,10 @@ int nb_clear_meshes(nb_ctx *c) {
     return 0;
 }
 
-static int upload_local(nb_ctx *c) {
-    cudaStream_t s = c->stream;
-#define UP(buf) CK(cudaMemcpyAsync(buf.d, buf.h, buf.bytes(), cudaMemcpyHostToDevice, s))
-    UP(c->nodes); UP(c->tris); UP(c->verts); UP(c->normals); UP(c->uvs); UP(c->faces); UP(c->dmeshes); UP(c->cdf); UP(c->emitters);
-#undef UP
-    CK(cudaStreamSynchronize(s));
+static int upload_local(nb_ctx *c) {        // the whole arena in ONE host->device copy
+    if (!c->arena_d || !c->arena_h) return fail("no host copy of the scene on this context");
+    CK(cudaMemcpyAsync(c->arena_d, c->arena_h, c->arena_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -496,10 +551,10 @@ int nb_upload_scene(nb_ctx *c) {
     if (c->leader) return fail("nb_upload_scene: call it on the group's leader context");
     if (!c->built) return fail("nb_build_accel has not been called");
     if (ensure_device(c)) return 1;
-    // ONE copy crosses PCIe; the other ranks of a group receive it over NVLink (ncclBroadcast)
-    if (c->comm_rank == 0 && upload_local(c)) return 1;
+    // a group uploads SHARDED: every rank sends 1/N of the arena over its own PCIe link, one in-place ncclAllGather over
+    // NVLink completes it on every device (nb_multi.inl)
     if (nbm::grouped(c)) return nbm::replicate_scene(c, false);
-    return 0;
+    return upload_local(c);
 }
 
 static int build_accel_local(nb_ctx *c);
@@ -515,19 +570,40 @@ int nb_build_accel(nb_ctx *c) {
     return 0;
 }
 
+#if NB_WIDE
+// Collapses a binary hierarchy (nb_bvh.h layout) into the 8-wide compressed one (nb_wide.h) and makes it the context's
+// nodes / triangles (device + pinned mirror).  bnodes / btris may alias the context's current mirrors.
+static int to_wide(nb_ctx *c, const float *bnodes, uint32_t n_bnodes, const float *btris, uint32_t n_btris) {
+    nb::WideOutput w; const char *err = nullptr;
+    if (!nb::build_wide(bnodes, n_bnodes, btris, n_btris, w, &err)) return fail("wide hierarchy: %s", err ? err : "conversion failed");
+    CK(c->nodes.alloc((size_t) w.nnodes * 5)); CK(c->tris.alloc(w.tris.size() / 4));
+    memcpy(c->nodes.h, w.nodes.data(), w.nodes.size() * sizeof(uint32_t));
+    if (!w.tris.empty()) memcpy(c->tris.h, w.tris.data(), w.tris.size() * sizeof(float));
+    CK(cudaMemcpyAsync(c->nodes.d, c->nodes.h, c->nodes.bytes(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tris.d, c->tris.h, c->tris.bytes(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_nodes = w.nnodes; c->top_nodes = 0; c->bvh_depth = w.depth; c->build_seconds += w.seconds;
+    return 0;
+}
+#endif
+
 static int build_accel_local(nb_ctx *c) {
     size_t nv = 0, nf = 0, ncdf = 0, nem = 0;
     for (auto &m : c->meshes) { nv += m.nv; nf += m.nf; if (m.emitter.type == NB_EMITTER_AREA) { ncdf += m.nf + 1; nem++; } }
     if (nf >= (1u << 28)) return fail("too many triangles (%zu)", nf);
-    CK(c->verts.alloc(nv)); CK(c->normals.alloc(nv)); CK(c->uvs.alloc(nv)); CK(c->faces.alloc(nf));
+    arena_release(c);
+    bool any_n = false, any_uv = false;
+    for (auto &m : c->meshes) { any_n = any_n || !m.N.empty(); any_uv = any_uv || !m.UV.empty(); }
+    // normals / texture coordinates only when some mesh has them (the kernels read them behind the per-mesh flags)
+    CK(c->verts.alloc(nv)); CK(c->normals.alloc(any_n ? nv : 0)); CK(c->uvs.alloc(any_uv ? nv : 0)); CK(c->faces.alloc(nf));
     CK(c->dmeshes.alloc(c->meshes.size())); CK(c->cdf.alloc(ncdf)); CK(c->emitters.alloc(nem));
     size_t vo = 0, fo = 0, co = 0, eo = 0;
     for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
         const HostMesh &m = c->meshes[mi];
         for (uint32_t i = 0; i < m.nv; ++i) {
             c->verts.h[vo + i] = make_float4(m.V[3 * i], m.V[3 * i + 1], m.V[3 * i + 2], 0.f);
-            c->normals.h[vo + i] = m.N.empty() ? make_float4(0, 0, 0, 0) : make_float4(m.N[3 * i], m.N[3 * i + 1], m.N[3 * i + 2], 0.f);
-            c->uvs.h[vo + i] = m.UV.empty() ? make_float2(0, 0) : make_float2(m.UV[2 * i], m.UV[2 * i + 1]);
+            if (any_n) c->normals.h[vo + i] = m.N.empty() ? make_float4(0, 0, 0, 0) : make_float4(m.N[3 * i], m.N[3 * i + 1], m.N[3 * i + 2], 0.f);
+            if (any_uv) c->uvs.h[vo + i] = m.UV.empty() ? make_float2(0, 0) : make_float2(m.UV[2 * i], m.UV[2 * i + 1]);
         }
         for (uint32_t f = 0; f < m.nf; ++f)
             c->faces.h[fo + f] = make_uint4((uint32_t) vo + m.F[3 * f], (uint32_t) vo + m.F[3 * f + 1], (uint32_t) vo + m.F[3 * f + 2], (uint32_t) mi);
@@ -587,6 +663,11 @@ static int build_accel_local(nb_ctx *c) {
         CK(cudaEventSynchronize(e1));
         float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
         c->build_seconds = ms * 1e-3; c->builder_used = 1;
+#if NB_WIDE
+        // the device builder leaves the binary layout in the pinned mirrors: collapse it on the host, replace nodes / triangles
+        if (to_wide(c, reinterpret_cast<const float *>(c->nodes.h), c->n_nodes, reinterpret_cast<const float *>(c->tris.h), (uint32_t) (c->tris.n / 3))) return 1;
+#endif
+        if (arena_pack(c)) return 1;
         c->built = true;
         return 0;
     }
@@ -605,11 +686,23 @@ static int build_accel_local(nb_ctx *c) {
     c->n_nodes = out.nnodes; c->top_nodes = out.top_nodes; c->bvh_depth = out.depth;
     c->build_seconds = out.build_seconds; c->builder_used = 0;
     if (out.depth >= nb::kStack) return fail("BVH too deep (%d)", out.depth);
+#if NB_WIDE
+    if (to_wide(c, out.nodes.data(), out.nnodes, out.tris.data(), (uint32_t) (out.tris.size() / 12))) return 1;
+#else
     CK(c->nodes.alloc((size_t) out.nnodes * 4)); CK(c->tris.alloc(out.tris.size() / 4));
     memcpy(c->nodes.h, out.nodes.data(), out.nodes.size() * sizeof(float));
     if (!out.tris.empty()) memcpy(c->tris.h, out.tris.data(), out.tris.size() * sizeof(float));
+#endif
+    {   // mesh tables to the device (nodes / tris follow inside arena_pack's copies: their device buffers are still empty)
+        cudaStream_t s = c->stream;
+#define UP(buf) CK(cudaMemcpyAsync(buf.d, buf.h, buf.bytes(), cudaMemcpyHostToDevice, s))
+        UP(c->nodes); UP(c->tris); UP(c->verts); UP(c->normals); UP(c->uvs); UP(c->faces); UP(c->dmeshes); UP(c->cdf); UP(c->emitters);
+#undef UP
+        CK(cudaStreamSynchronize(s));
+    }
+    if (arena_pack(c)) return 1;
     c->built = true;
-    return upload_local(c);
+    return 0;
 }
 
 int nb_set_accel_cache(nb_ctx *c, const char *path) {
@@ -756,6 +849,7 @@ int nb_last_kernel_ms(nb_ctx *c, double *ms) {
 
 int nb_render(nb_ctx *c, float *film_host, nb_stats *st) {
     if (!c || (!film_host && !(nbm::grouped(c) && c->comm_rank != 0))) return fail("null argument");
+    if (c->prog_active) return fail("nb_render inside a progressive frame (nb_render_end first)");
     if (ensure_device(c)) return 1;
     const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
     if (film_elems > c->film_cap) {
@@ -960,6 +1054,74 @@ int nb_film_to_rgb(nb_ctx *c, const float *film_host, float *rgb_host) {
     return rc;
 }
 
+// ---- progressive frames (stands where NoriScreen refreshes from the shared ImageBlock while the tiles render, ref: src/gui.cpp:120-138)
+int nb_render_begin(nb_ctx *c) {
+    if (!c) return fail("null context");
+    if (nbm::grouped(c)) return fail("progressive frames run on a single-device context");
+    if (ensure_device(c)) return 1;
+    if (!c->have_camera) return fail("nb_set_camera has not been called");
+    if (c->seed_mode != NB_SEED_PER_SAMPLE) return fail("progressive frames need per-(pixel, sample) sampler streams (NB_SEED_PER_SAMPLE)");
+    const int n_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, nullptr, nullptr);
+    const int edge = NB_BLOCK_SIZE + 2 * c->border;
+    const size_t blk_elems = (size_t) n_tiles * edge * edge;
+    if (blk_elems > c->blocks_cap) {
+        if (c->blocks) cudaFree(c->blocks);
+        c->blocks = nullptr; c->blocks_cap = 0;
+        CK(cudaMalloc(&c->blocks, sizeof(float4) * (blk_elems ? blk_elems : 1)));
+        c->blocks_cap = blk_elems;
+    }
+    if (blk_elems) CK(cudaMemsetAsync(c->blocks, 0, sizeof(float4) * blk_elems, c->stream));
+    c->prog_active = true; c->prog_done = 0; c->prog_pass = 0; c->film_valid = false;
+    memset(&c->prog_stats, 0, sizeof c->prog_stats);
+    return 0;
+}
+
+int nb_render_pass(nb_ctx *c, uint32_t n_samples, nb_stats *st) {
+    if (!c) return fail("null context");
+    if (!c->prog_active) return fail("nb_render_pass: call nb_render_begin first");
+    if (ensure_device(c)) return 1;
+    if (n_samples == 0 || c->prog_done + n_samples > c->spp) return fail("nb_render_pass: %u samples asked, %u of %u left", n_samples, c->spp - c->prog_done, c->spp);
+    c->prog_pass = n_samples;
+    nb_stats ps; memset(&ps, 0, sizeof ps);
+    int n_tiles = 0;
+    if (render_tiles(c, nullptr, c->stream, &ps, &n_tiles)) { c->prog_active = false; return 1; }
+    if (finish_stats(c, c->stream, &ps, 0)) { c->prog_active = false; return 1; }
+    c->prog_done += n_samples;
+    nb_stats &a = c->prog_stats;
+    a.samples += ps.samples; a.rays += ps.rays; a.node_visits += ps.node_visits; a.tri_tests += ps.tri_tests; a.hits_shaded += ps.hits_shaded;
+    a.kernel_ms += ps.kernel_ms; a.total_ms += ps.total_ms; a.launches += ps.launches;
+    if (st) *st = a;
+    return 0;
+}
+
+int nb_render_preview(nb_ctx *c, float *film_host, uint8_t *rgb8_host) {
+    if (!c) return fail("null context");
+    if (!c->prog_active) return fail("nb_render_preview: call nb_render_begin first");
+    if (ensure_device(c)) return 1;
+    const size_t film_elems = (size_t) (c->W + 2 * c->border) * (c->H + 2 * c->border);
+    if (film_elems > c->film_cap) {
+        if (c->film) cudaFree(c->film);
+        c->film = nullptr; c->film_cap = 0;
+        CK(cudaMalloc(&c->film, sizeof(float4) * (film_elems ? film_elems : 1)));
+        c->film_cap = film_elems;
+    }
+    cudaStream_t s = c->stream;
+    const int n_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, nullptr, nullptr);
+    CK(cudaMemsetAsync(c->film, 0, sizeof(float4) * film_elems, s));
+    if (merge(c, c->blocks, n_tiles, c->tile_rank, c->tile_nranks, c->film, s)) return 1;
+    if (film_host) CK(cudaMemcpyAsync(film_host, c->film, sizeof(float4) * film_elems, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->film_valid = true;
+    if (rgb8_host) return nb_last_film_to_srgb8(c, rgb8_host);
+    return 0;
+}
+
+int nb_render_end(nb_ctx *c) {
+    if (!c) return fail("null context");
+    c->prog_active = false; c->prog_done = 0; c->prog_pass = 0;
+    return 0;
+}
+
 int nb_last_film_to_srgb8(nb_ctx *c, uint8_t *rgb8_host) {
     if (!c || !rgb8_host) return fail("null argument");
     if (c->leader) return fail("nb_last_film_to_srgb8: call it on the group's leader context");
@@ -983,7 +1145,12 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail("null argument");
     std::string k(key);
     if (k == "blocks_per_sm") c->opt_blocks_per_sm = value;
-    else if (k == "smem_nodes") c->opt_smem_nodes = value;
+    else if (k == "smem_nodes") {
+#if NB_WIDE
+        if (value != 0) return fail("smem_nodes stages 64-byte binary nodes; this build walks the 8-wide hierarchy");
+#endif
+        c->opt_smem_nodes = value;
+    }
     else if (k == "chunk") c->opt_chunk = value;
     else if (k == "count") c->opt_count = value;
     else if (k == "prefetch") c->opt_prefetch = value;
@@ -991,7 +1158,12 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     else if (k == "wf_pool") { if (value < 128 || value > (1ll << 28)) return fail("wf_pool must be in [128, 2^28]"); c->opt_wf_pool = value; }
     else if (k == "wf_check") { if (value < 1 || value > 1024) return fail("wf_check must be in [1, 1024]"); c->opt_wf_check = value; }
     else if (k == "occ_tail") { if (value < 0 || value > 31) return fail("occ_tail must be in [0, 31]"); c->opt_occ_tail = value; }
-    else if (k == "max_leaf") { c->opt_max_leaf = value; c->built = false; }
+    else if (k == "max_leaf") {
+#if NB_WIDE
+        if (value < 1 || value > 3) return fail("max_leaf must be in [1, 3] (a leaf child of a wide node holds 1..3 triangles)");
+#endif
+        c->opt_max_leaf = value; c->built = false;
+    }
     else if (k == "bfs_nodes") { c->opt_bfs_nodes = value; c->built = false; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail("builder must be 0 (host SAH) or 1 (device LBVH)"); c->opt_builder = value; c->built = false; }
     else return fail("unknown option \"%s\"", key);

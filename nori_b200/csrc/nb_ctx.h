@@ -25,12 +25,18 @@ struct HostMesh {
 template <typename T>
 struct DevBuf {
     T *d = nullptr; T *h = nullptr; size_t n = 0;   // device + pinned host mirror (h stays null for device-only buffers)
-    void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = nullptr; h = nullptr; n = 0; }
+    bool view = false;                               // a window into the context's scene arena: not owned
+    void release() { if (!view) { if (d) cudaFree(d); if (h) cudaFreeHost(h); } d = nullptr; h = nullptr; n = 0; view = false; }
     cudaError_t alloc(size_t count, bool with_host = true) {
         release(); n = count;
         size_t bytes = sizeof(T) * (count ? count : 1);
         cudaError_t e = cudaMalloc(&d, bytes); if (e != cudaSuccess) return e;
         return with_host ? cudaMallocHost(&h, bytes) : cudaSuccess;
+    }
+    void set_view(char *dev_base, char *host_base, size_t offset, size_t count) {
+        release();
+        d = reinterpret_cast<T *>(dev_base + offset); h = host_base ? reinterpret_cast<T *>(host_base + offset) : nullptr;
+        n = count; view = true;
     }
     size_t bytes() const { return sizeof(T) * n; }
 };
@@ -50,6 +56,11 @@ struct nb_ctx {
     nbi::DevBuf<nb::DevMesh> dmeshes;
     nbi::DevBuf<float> cdf;
     nbi::DevBuf<int32_t> emitters;
+    // After a build the nine tables are windows into ONE allocation (the scene arena): one host->device copy uploads the scene,
+    // one ncclBroadcast replicates it, and a group re-uploads it SHARDED -- every rank sends 1/N over its own PCIe link and one
+    // in-place ncclAllGather over NVLink completes it (nb_multi.inl).
+    char *arena_d = nullptr, *arena_h = nullptr; size_t arena_bytes = 0;
+    char *shard_h = nullptr; size_t shard_cap = 0;   // process-per-GPU ranks > 0: pinned copy of this rank's shard of the arena
     uint32_t n_nodes = 0, n_prims = 0, top_nodes = 0; int bvh_depth = 0; bool built = false;
     double build_seconds = 0;
     // camera / film / sampler / integrator
@@ -70,6 +81,7 @@ struct nb_ctx {
     // wavefront engine (nb_wave.cu): path pool (structure of arrays), extension queue, occlusion queue, counters
     float4 *wf_cols = nullptr, *wf_shadow = nullptr; uint32_t *wf_ext = nullptr, *wf_ctr = nullptr, *wf_ctr_h = nullptr; size_t wf_cap = 0;
     int64_t opt_wf_pool = 1 << 21, opt_wf_check = 4;
+    bool prog_active = false; uint32_t prog_done = 0, prog_pass = 0; nb_stats prog_stats = {};   // progressive frame (nb_render_begin .. nb_render_end)
     int64_t opt_prefetch = 0;          // L2 warm-up of nodes + triangles before the render kernel (l2_prefetch_kernel)
     int builder_used = 0;   // 0 host SAH, 1 device LBVH
     std::string accel_cache; bool accel_cache_hit = false;   // on-disk hierarchy cache (nb_set_accel_cache)

@@ -16,6 +16,7 @@
 // Optionally the top of the BVH is staged into shared memory once per CTA with a TMA bulk copy (cp.async.bulk).
 #pragma once
 #include "nb_device.cuh"
+#include "nb_wide.h"
 
 namespace nb {
 
@@ -53,6 +54,17 @@ namespace nb {
 #define NB_STACK 64
 #endif
 constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
+#ifndef NB_WIDE
+#define NB_WIDE 0            // 1: the walk runs on the 8-wide compressed hierarchy (nb_wide.h) instead of the binary one
+#endif
+#ifndef NB_WIDE_POSTPONE
+#define NB_WIDE_POSTPONE 0   // wide walk: triangles are tested only once this many lanes of the warp hold some (0: at once)
+#endif
+#if NB_WIDE
+typedef uint2 StackT; constexpr int kStackN = kWideStack;
+#else
+typedef int StackT; constexpr int kStackN = kStack;
+#endif
 constexpr int kBlockEdgeMax = 32 + 2 * 8;
 
 struct SceneDev {
@@ -97,7 +109,7 @@ struct RenderParams {
     // wavefront engine (nb_wave.cu / nb_wave.cuh; unused by the other kernels)
     float4 *occ_queue;              // occlusion queue: 3 x float4 per ray (origin | mint, direction | maxt, radiance | slot)
     uint32_t occ_capacity;          // rays the queue holds (= wf_pool)
-    int32_t reserved0;
+    uint32_t sample_offset;         // progressive frames: this pass renders the sample streams sample_offset .. sample_offset + spp - 1 of every pixel
     float4 *wf_cols;                // path pool, structure of arrays: kWfCols columns of wf_pool float4 each
     uint32_t *wf_ext;               // queue of pool slots whose extension ray waits to be traced
     uint32_t *wf_ctr;               // engine counters (nb_wave.cuh: WF_*)
@@ -181,9 +193,101 @@ __device__ __forceinline__ bool leaf_test(const SceneDev &sc, int leaf, Ray &r, 
     return false;
 }
 
+#if NB_WIDE
+// One triangle of the wide layout (same 48-byte record, same operation sequence as leaf_test).  Returns true when an any-hit
+// query is answered.
+__device__ __forceinline__ bool tri_test_one(const SceneDev &sc, unsigned idx, Ray &r, Trav &t, bool any_hit) {
+    const float4 a = __ldg(&sc.tris[(size_t) idx * 3 + 0]);
+    const float4 b = __ldg(&sc.tris[(size_t) idx * 3 + 1]);
+    const float4 c = __ldg(&sc.tris[(size_t) idx * 3 + 2]);
+    const V3 o = mk(r.ox, r.oy, r.oz), d = mk(r.dx, r.dy, r.dz);
+    const V3 p0 = xyz(a);
+    const V3 edge1 = xyz(b) - p0, edge2 = xyz(c) - p0;
+    const V3 pvec = cross(d, edge2);
+    const float det = dot(edge1, pvec);
+    if (det > -1e-8f && det < 1e-8f) return false;
+    const float inv_det = 1.0f / det;
+    const V3 tvec = o - p0;
+    const float u = dot(tvec, pvec) * inv_det;
+    if (u < 0.0f || u > 1.0f) return false;
+    const V3 qvec = cross(tvec, edge1);
+    const float v = dot(d, qvec) * inv_det;
+    if (v < 0.0f || u + v > 1.0f) return false;
+    const float tt = dot(edge2, qvec) * inv_det;
+    if (!(tt >= r.mint && tt <= r.maxt)) return false;
+    const uint32_t prim = __float_as_uint(a.w);
+    if (any_hit) { t.hprim = prim; return true; }
+    if (t.hprim == 0xffffffffu || tt < r.maxt || prim > t.hprim) { r.maxt = tt; t.hu = u; t.hv = v; t.hprim = prim; }
+    return false;
+}
+
+// The walk over the 8-wide compressed hierarchy (nb_wide.h).  Same contract as the binary trav_run below: closest hit with the
+// reference's tie rule or any hit, hit in (t.hprim, t.hu, t.hv, r.maxt); with tail > 0 (wavefront engine) the walk is
+// suspended -- its pending groups pushed on the stack, t.node = 1 -- once at most `tail` lanes of the warp are still walking.
+template <bool COUNT, bool TMA_TOP>
+__device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *, int, Ray &r, Trav &t,
+                                         StackT *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris, int tail = 0) {
+    WideRay R;
+    R.idx = t.idx; R.idy = t.idy; R.idz = t.idz; R.ox = r.ox; R.oy = r.oy; R.oz = r.oz;
+    R.negx = t.idx < 0.f; R.negy = t.idy < 0.f; R.negz = t.idz < 0.f;
+    const uint32_t octinv = 7u - ((R.negx ? 1u : 0u) | (R.negy ? 2u : 0u) | (R.negz ? 4u : 0u));
+    R.octinv4 = octinv * 0x01010101u;
+    uint2 ng = make_uint2(0u, 0x80000000u), tg = make_uint2(0u, 0u);
+    int sp = 0;
+    if (t.node != kDone && t.node != 0) { ng = make_uint2(0u, 0u); sp = t.sp; }        // resumed: its groups are on the stack
+    bool suspended = false;
+    const uint4 *wn = reinterpret_cast<const uint4 *>(sc.nodes);
+    for (;;) {
+        if (ng.y > 0x00ffffffu) {
+            const uint32_t imask = ng.y & 0xffu;
+            const int bit = wide_bfind(ng.y);
+            const uint32_t base = ng.x;
+            ng.y &= ~(1u << bit);
+            if (ng.y > 0x00ffffffu) stack[sp++] = ng;
+            const uint32_t slot = ((uint32_t) (bit - 24)) ^ octinv;
+            const uint32_t ni = base + (uint32_t) __popc(imask & ~(0xffffffffu << slot));
+            uint32_t cb, tb, im;
+            const uint32_t hm = wide_node_test([&](uint32_t *w) {
+                const uint4 *q = wn + (size_t) ni * 5;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { const uint4 v = __ldg(q + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+            }, R, r.mint, r.maxt, cb, tb, im);
+            if (COUNT) n_nodes++;
+            ng = make_uint2(cb, (hm & 0xff000000u) | im);
+            tg = make_uint2(tb, hm & 0x00ffffffu);
+        } else {
+            tg = ng; ng = make_uint2(0u, 0u);
+        }
+#if NB_WIDE_POSTPONE
+        // postpone the triangles while few lanes hold some and this lane still has nodes to visit
+        if (tg.y != 0u && ng.y > 0x00ffffffu && __popc(__ballot_sync(__activemask(), tg.y != 0u)) < NB_WIDE_POSTPONE) { stack[sp++] = tg; tg.y = 0u; }
+#endif
+        bool answered = false;
+        while (tg.y != 0u) {
+            const int ti = wide_bfind(tg.y);
+            tg.y &= ~(1u << ti);
+            if (COUNT) n_tris++;
+            if (tri_test_one(sc, tg.x + (unsigned) ti, r, t, any_hit)) { answered = true; break; }
+        }
+        if (answered) break;
+        if (ng.y <= 0x00ffffffu) {
+            if (sp > 0) ng = stack[--sp];
+            else break;
+        }
+#if NB_WAVEFRONT
+        if (tail > 0 && __popc(__activemask()) <= tail) {
+            if (ng.y != 0u) stack[sp++] = ng;          // a node group with hits left, or a popped triangle group
+            suspended = true;
+            break;
+        }
+#endif
+    }
+    if (suspended) { t.node = 1; t.sp = sp; } else { t.node = kDone; t.sp = 0; }
+}
+#else
 template <bool COUNT, bool TMA_TOP>
 __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snodes, int smem_nodes, Ray &r, Trav &t,
-                                         int *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris, int tail = 0) {
+                                         StackT *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris, int tail = 0) {
     int node = t.node, sp = t.sp;
     int parked = 0;                  // postponed leaf ref (leaf refs are negative; 0 = none)
     bool suspended = false;
@@ -261,13 +365,14 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
     }
     if (suspended) { t.node = node; t.sp = sp; } else { t.node = kDone; t.sp = 0; }
 }
+#endif   // NB_WIDE
 
 // Resumable walk (wavefront engine): tr.node == kDone on entry means a fresh ray; otherwise (node, sp, stack) and the
 // closest hit so far continue from where a tail cut suspended them.  The slab-test reciprocals are recomputed per call
 // so that only (node, sp, hit) stay live across the shading phase.
 template <bool COUNT, bool TMA_TOP>
 __device__ __forceinline__ void walk_wave(const float4 *nodes, const float4 *tris, const float4 *snodes, int smem_nodes,
-                                          Ray &ray, Trav &tr, int *stack, bool any_hit, int tail, unsigned &nn, unsigned &nt) {
+                                          Ray &ray, Trav &tr, StackT *stack, bool any_hit, int tail, unsigned &nn, unsigned &nt) {
     SceneDev sc;
     sc.nodes = nodes; sc.tris = tris;
     const int node = tr.node, sp = tr.sp;
@@ -291,7 +396,7 @@ struct WalkResult { float t, u, v; uint32_t prim; unsigned n_nodes, n_tris; };
 template <bool COUNT, bool TMA_TOP>
 __device__ NB_WALK_ATTR WalkResult walk(const float4 *nodes, const float4 *tris, const float4 *snodes, int smem_nodes,
                                         float ox, float oy, float oz, float mint, float dx, float dy, float dz, float maxt, bool any_hit) {
-    int stack[kStack];
+    StackT stack[kStackN];
     SceneDev sc;
     sc.nodes = nodes; sc.tris = tris;
     Ray r; r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.mint = mint; r.maxt = maxt;
@@ -675,7 +780,7 @@ __device__ __forceinline__ bool shade(const RenderParams &P, Path &ps, Ray &ray,
 __device__ __forceinline__ void begin_path(const RenderParams &P, Path &ps, Ray &ray, int px, int py, uint32_t sample) {
     if (P.seed_mode == 0) {
         const uint64_t pix = (uint64_t) py * (uint64_t) P.W + (uint64_t) px;
-        pcg_seed(ps.rng, (P.seed << 32) + pix, (uint64_t) sample);
+        pcg_seed(ps.rng, (P.seed << 32) + pix, (uint64_t) sample + (uint64_t) P.sample_offset);
     } else if (P.block_stream_skip) {
         // reference per-block stream (ref: src/independent.cpp:36-41) for integrators with a FIXED number of draws per
         // sample (normals: the 4 camera draws): sample j of the block sits at stream position 4*j, reached by skip-ahead
@@ -877,7 +982,7 @@ template <int INTEG, bool COUNT>
 __global__ void __launch_bounds__(32) render_block_mode_kernel(const __grid_constant__ RenderParams P) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= P.n_my_tiles) return;
-    int stack[kStack];
+    StackT stack[kStackN];
     Path ps; Ray ray; Trav tr;
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
     const int tile_id = P.tile_rank + slot * P.tile_nranks;
@@ -906,7 +1011,7 @@ __global__ void __launch_bounds__(32) render_block_mode_kernel(const __grid_cons
 // (oracle.c: orc_li_samples).  One thread per path: a test utility, not a throughput path.
 template <int INTEG>
 __global__ void __launch_bounds__(128) li_samples_kernel(const __grid_constant__ RenderParams P, unsigned long long n, float *lum) {
-    int stack[kStack];
+    StackT stack[kStackN];
     Path ps; Ray ray; Trav tr;
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
     for (unsigned long long k = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; k < n;
@@ -978,7 +1083,7 @@ struct HitOut { float t, u, v; uint32_t prim; uint32_t mesh; };
 template <bool COUNT>
 __global__ void __launch_bounds__(128) intersect_kernel(SceneDev sc, const float4 *rays, unsigned long long n, HitOut *hits,
                                                         int shadow, float *full16, unsigned long long *counters) {
-    int stack[kStack];
+    StackT stack[kStackN];
     unsigned n_nodes = 0, n_tris = 0, n_rays = 0;
     for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long) gridDim.x * blockDim.x) {

@@ -3,8 +3,8 @@
 // Replaces the reference's tile loop + merge (ref: src/main.cpp:85-113, src/block.cpp:93-102) for N devices: 32x32 image
 // tiles are sharded tile_id % N (BlockGenerator's role, ref: src/block.cpp:119-152); every device renders its tiles into
 // packed ImageBlocks; ONE grouped ncclSend/ncclRecv per frame gathers the finished blocks on rank 0 over NVLink (NCCL has
-// no native gather); ONE merge launch adds them into the film.  The scene arrays are built once (rank 0) and replicated
-// with ncclBroadcast over NVLink instead of N host->device uploads over PCIe.
+// no native gather); ONE merge launch adds them into the film.  The scene (one arena, nb_ctx.h) is built once (rank 0) and
+// replicated with ONE ncclBroadcast over NVLink; re-uploads are sharded (1/N per PCIe link + ONE in-place ncclAllGather).
 //
 // Two ways to form the group, same code underneath:
 //   nb_create_multi(devices, n)            one process drives n devices (ncclCommInitAll) -- what `nori --gpus n` uses
@@ -30,6 +30,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -42,7 +43,7 @@ NcclApi &nccl() {
 #define NB_SYM(field, name) do { *(void **) (&x.field) = dlsym(x.handle, name); if (!x.field) { x.err = std::string("libnccl lacks ") + name; return x; } } while (0)
         NB_SYM(GetUniqueId, "ncclGetUniqueId"); NB_SYM(CommInitRank, "ncclCommInitRank"); NB_SYM(CommInitAll, "ncclCommInitAll");
         NB_SYM(CommDestroy, "ncclCommDestroy"); NB_SYM(GroupStart, "ncclGroupStart"); NB_SYM(GroupEnd, "ncclGroupEnd");
-        NB_SYM(Send, "ncclSend"); NB_SYM(Recv, "ncclRecv"); NB_SYM(Broadcast, "ncclBroadcast"); NB_SYM(GetErrorString, "ncclGetErrorString");
+        NB_SYM(Send, "ncclSend"); NB_SYM(Recv, "ncclRecv"); NB_SYM(Broadcast, "ncclBroadcast"); NB_SYM(AllGather, "ncclAllGather"); NB_SYM(GetErrorString, "ncclGetErrorString");
 #undef NB_SYM
         return x;
     }();
@@ -68,16 +69,20 @@ std::vector<nb_ctx *> locals(nb_ctx *c) {
 
 bool grouped(const nb_ctx *c) { return c->comm != nullptr && c->comm_nranks > 1; }
 
-// Replicates the built scene of rank 0 on every rank: a 16-word header (array sizes + hierarchy facts), then the nine
-// arrays, each one ncclBroadcast over NVLink.  Ranks other than 0 hold device-only buffers.
+// Replicates the built scene of rank 0 on every rank (with_header): a 16-word header (table sizes + hierarchy facts), then
+// the scene arena in ONE ncclBroadcast over NVLink.  Ranks other than 0 hold device-only tables; a process-per-GPU rank also
+// keeps a pinned copy of ITS shard of the arena for later re-uploads.
+// Re-upload (!with_header): SHARDED -- every rank copies 1/N of the arena host->device over its own PCIe link, one in-place
+// ncclAllGather over NVLink completes the arena on every device.
 int replicate_scene(nb_ctx *c, bool with_header) {
     if (need_nccl()) return 1;
     NcclApi &N = nccl();
     std::vector<nb_ctx *> L = locals(c);
+    const int nranks = c->comm_nranks;
     constexpr int kHdr = 16;
-    std::vector<unsigned long long *> hd(L.size(), nullptr);
-    auto cleanup = [&]() { for (size_t i = 0; i < L.size(); ++i) if (hd[i]) { cudaSetDevice(L[i]->device); cudaFree(hd[i]); } };
     if (with_header) {
+        std::vector<unsigned long long *> hd(L.size(), nullptr);
+        auto cleanup = [&]() { for (size_t i = 0; i < L.size(); ++i) if (hd[i]) { cudaSetDevice(L[i]->device); cudaFree(hd[i]); } };
         for (size_t i = 0; i < L.size(); ++i) {
             nb_ctx *x = L[i];
             CK(cudaSetDevice(x->device));
@@ -86,7 +91,7 @@ int replicate_scene(nb_ctx *c, bool with_header) {
                 if (!x->built) { cleanup(); return fail("replicate_scene: rank 0 has no built scene"); }
                 unsigned long long h[kHdr] = { x->nodes.n, x->tris.n, x->verts.n, x->normals.n, x->uvs.n, x->faces.n, x->dmeshes.n, x->cdf.n,
                                                x->emitters.n, x->n_nodes, x->n_prims, x->top_nodes, (unsigned long long) x->bvh_depth,
-                                               (unsigned long long) x->builder_used, 0, 0 };
+                                               (unsigned long long) x->builder_used, x->arena_bytes, 0 };
                 CK(cudaMemcpyAsync(hd[i], h, sizeof h, cudaMemcpyHostToDevice, x->stream));
                 CK(cudaStreamSynchronize(x->stream));
             }
@@ -104,25 +109,61 @@ int replicate_scene(nb_ctx *c, bool with_header) {
             unsigned long long h[kHdr];
             CK(cudaMemcpyAsync(h, hd[i], sizeof h, cudaMemcpyDeviceToHost, x->stream));
             CK(cudaStreamSynchronize(x->stream));
-            CK(x->nodes.alloc(h[0], false)); CK(x->tris.alloc(h[1], false)); CK(x->verts.alloc(h[2], false)); CK(x->normals.alloc(h[3], false));
-            CK(x->uvs.alloc(h[4], false)); CK(x->faces.alloc(h[5], false)); CK(x->dmeshes.alloc(h[6], false)); CK(x->cdf.alloc(h[7], false));
-            CK(x->emitters.alloc(h[8], false));
+            size_t counts[9], offs[9];
+            for (int k = 0; k < 9; ++k) counts[k] = (size_t) h[k];
+            const size_t total = arena_layout(counts, offs);
+            if (total != (size_t) h[14]) { cleanup(); return fail("replicate_scene: arena layout mismatch between ranks (%zu vs %llu bytes)", total, h[14]); }
+            arena_release(x);
+            CK(cudaMalloc(&x->arena_d, total + kArenaSlack));
+            x->arena_bytes = total;
+            arena_views(x, counts, offs);
             x->n_nodes = (uint32_t) h[9]; x->n_prims = (uint32_t) h[10]; x->top_nodes = (uint32_t) h[11]; x->bvh_depth = (int) h[12];
             x->builder_used = (int) h[13]; x->build_seconds = 0; x->built = true;
         }
         cleanup();
+        NCK(N.GroupStart());
+        for (nb_ctx *x : L) {
+            CK(cudaSetDevice(x->device));
+            NCK(N.Broadcast(x->arena_d, x->arena_d, x->arena_bytes, ncclChar, 0, (ncclComm_t) x->comm, x->stream));
+        }
+        NCK(N.GroupEnd());
     }
-    for (nb_ctx *x : L) if (!x->built) return fail("replicate_scene: rank %d has no scene buffers (nb_build_accel first)", x->comm_rank);
-#define NB_BCAST(buf) do { \
-        if (L[0]->buf.n) { \
-            NCK(N.GroupStart()); \
-            for (nb_ctx *x : L) { CK(cudaSetDevice(x->device)); \
-                NCK(N.Broadcast(x->buf.d, x->buf.d, x->buf.bytes(), ncclChar, 0, (ncclComm_t) x->comm, x->stream)); } \
-            NCK(N.GroupEnd()); \
-        } } while (0)
-    NB_BCAST(nodes); NB_BCAST(tris); NB_BCAST(verts); NB_BCAST(normals); NB_BCAST(uvs); NB_BCAST(faces); NB_BCAST(dmeshes); NB_BCAST(cdf); NB_BCAST(emitters);
-#undef NB_BCAST
+    for (nb_ctx *x : L) if (!x->built || !x->arena_d) return fail("replicate_scene: rank %d has no scene buffers (nb_build_accel first)", x->comm_rank);
+    const size_t B = c->arena_bytes;
+    const size_t S = ((B + (size_t) nranks - 1) / (size_t) nranks + kArenaAlign - 1) / kArenaAlign * kArenaAlign;     // shard bytes; nranks * S <= B + slack
+    if (with_header) {
+        // process-per-GPU ranks > 0: keep this rank's shard in pinned host memory (the source of later sharded uploads)
+        for (nb_ctx *x : L) {
+            if (x->comm_rank == 0 || x->leader) continue;
+            CK(cudaSetDevice(x->device));
+            if (S > x->shard_cap) {
+                if (x->shard_h) cudaFreeHost(x->shard_h);
+                x->shard_h = nullptr; x->shard_cap = 0;
+                CK(cudaMallocHost(&x->shard_h, S));
+                x->shard_cap = S;
+            }
+            const size_t off = (size_t) x->comm_rank * S;
+            const size_t n = off < B ? std::min(S, B - off) : 0;
+            if (n) CK(cudaMemcpyAsync(x->shard_h, x->arena_d + off, n, cudaMemcpyDeviceToHost, x->stream));
+        }
+    } else {
+        for (nb_ctx *x : L) {
+            CK(cudaSetDevice(x->device));
+            const size_t off = (size_t) x->comm_rank * S;
+            const size_t n = off < B ? std::min(S, B - off) : 0;
+            const char *src = x->arena_h ? x->arena_h + off : (x->leader && x->leader->arena_h ? x->leader->arena_h + off : x->shard_h);
+            if (n && !src) return fail("replicate_scene: rank %d has no host copy of its scene shard", x->comm_rank);
+            if (n) CK(cudaMemcpyAsync(x->arena_d + off, src, n, cudaMemcpyHostToDevice, x->stream));
+        }
+        NCK(N.GroupStart());
+        for (nb_ctx *x : L) {
+            CK(cudaSetDevice(x->device));
+            NCK(N.AllGather(x->arena_d + (size_t) x->comm_rank * S, x->arena_d, S, ncclChar, (ncclComm_t) x->comm, x->stream));
+        }
+        NCK(N.GroupEnd());
+    }
     for (nb_ctx *x : L) { CK(cudaSetDevice(x->device)); CK(cudaStreamSynchronize(x->stream)); }
+    CK(cudaSetDevice(c->device));
     return 0;
 }
 

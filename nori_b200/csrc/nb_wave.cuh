@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128, NB_MIN_BLOCKS) wf_trace_kernel(const __gr
     const unsigned lt_mask = (1u << lane) - 1u;
     const size_t N = P.wf_pool;
     float4 *C = P.wf_cols;
-    int stack[kStack + 1];
+    StackT stack[kStackN + 1];
     unsigned n_nodes = 0, n_tris = 0;
     const long long wd_t0 = clock64();
     for (int phase = 0; phase < 2; ++phase) {

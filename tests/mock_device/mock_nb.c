@@ -23,9 +23,14 @@ static double env_double(const char *name, double dflt) { const char *v = getenv
 const char *nb_last_error(void) { return g_err; }
 nb_ctx *nb_create(int device) { (void) device; return (nb_ctx *) calloc(1, sizeof(nb_ctx)); }
 void nb_destroy(nb_ctx *c) { free(c); }
+int nb_node_bytes(void) { return 64; }
 nb_ctx *nb_create_multi(const int *devices, int ndev) { (void) ndev; return nb_create(devices ? devices[0] : 0); }
 int nb_set_accel_cache(nb_ctx *c, const char *path) { (void) c; (void) path; return 0; }
 int nb_last_film_to_srgb8(nb_ctx *c, uint8_t *rgb8) { (void) c; (void) rgb8; return 1; }
+int nb_render_begin(nb_ctx *c) { (void) c; return 1; }
+int nb_render_pass(nb_ctx *c, uint32_t n, nb_stats *st) { (void) c; (void) n; (void) st; return 1; }
+int nb_render_preview(nb_ctx *c, float *f, uint8_t *r) { (void) c; (void) f; (void) r; return 1; }
+int nb_render_end(nb_ctx *c) { (void) c; return 0; }
 int nb_set_option(nb_ctx *c, const char *k, int64_t v) { (void) c; (void) k; (void) v; return 0; }
 int nb_add_mesh(nb_ctx *c, const float *V, uint32_t nv, const float *N, const float *UV, const uint32_t *F, uint32_t nf,
                 const nb_bsdf_desc *b, const nb_emitter_desc *e) { (void) c; (void) V; (void) nv; (void) N; (void) UV; (void) F; (void) nf; (void) b; (void) e; return 0; }

@@ -150,3 +150,37 @@ def test_hierarchy_cache_on_the_render_path(tmp_path, oracle):
     f1, s1 = hs.render(0, accel_cache=tmp_path / "ajax.nbbvh")
     f2, s2 = hs.render(0, accel_cache=tmp_path / "ajax.nbbvh")
     assert (tmp_path / "ajax.nbbvh").exists() and s1.rays == s2.rays and S.rel_l2(f2, f1) < 1e-6
+
+
+def test_progressive_frame_previews_and_final_film(tmp_path, oracle):
+    """SURVEY 8f row 4 (progressive preview in place of NoriScreen, ref: src/gui.cpp:120-138): a frame rendered in passes;
+    every preview is the film of the samples done so far, the last one is nb_render's frame."""
+    sc = S.config_cbox(96, 80, 16, S.INT_PATH_MIS)
+    with abi.Context(0) as ctx:
+        ctx.load(sc)
+        ref, st_ref = ctx.render()
+        seen = []
+        for done, film, rgb8, st in ctx.render_progressive(5, want_rgb8=True):      # passes of 5, 5, 5, 1 samples
+            seen.append(done)
+            sc_k = S.config_cbox(96, 80, done, S.INT_PATH_MIS)
+            ofilm, ost = oracle.OracleScene(sc_k).render(accel=1)                    # the first `done` sample streams of every pixel
+            assert st.rays == ost.rays and S.rel_l2(film, ofilm) <= 1e-4
+            assert rgb8.max() == 255 and rgb8.shape == (80, 96, 3)
+        assert seen == [5, 10, 15, 16]
+        assert st.rays == st_ref.rays and S.rel_l2(film, ref) <= 1e-6
+        ctx.set_option("engine", 2)                                                  # the wavefront engine accumulates passes the same way
+        for done, film, _, st in ctx.render_progressive(8):
+            pass
+        ctx.set_option("engine", 0)
+        assert st.rays == st_ref.rays and S.rel_l2(film, ref) <= 1e-6
+        film2, st2 = ctx.render()                                                    # and a plain frame afterwards is unaffected
+        assert st2.rays == st_ref.rays and S.rel_l2(film2, ref) <= 1e-6
+    path = host.write_xml(sc, str(tmp_path), "cbox")
+    if not os.path.exists(host.CLI_PATH):
+        from nori_b200 import build as nb_build
+        nb_build.build_host(force=True)
+    r = subprocess.run([host.CLI_PATH, path, "--no-gui", "--preview", "6"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    import cv2
+    a, b = cv2.imread(str(tmp_path / "cbox.png")), cv2.imread(str(tmp_path / "cbox_preview.png"))
+    assert a is not None and b is not None and np.array_equal(a, b)                 # the last preview IS the final image

@@ -29,6 +29,8 @@ for sc in (S.config_cbox(256, 192, 16, S.INT_PATH_MIS), S.Scene([S.ajax_standin(
     ctx.load(sc)            # rank 0 builds the hierarchy, the others receive the arrays over NVLink
     film = torch.zeros(sc.film_shape, dtype=torch.float32, device=dev) if rank == 0 else None
     st = ctx.render_gather(film.data_ptr() if rank == 0 else 0)
+    ctx.upload()            # sharded re-upload: 1/N per PCIe link + one in-place ncclAllGather; the frame must not change
+    st = ctx.render_gather(film.data_ptr() if rank == 0 else 0)
     rays = torch.tensor([st.rays], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(rays)
