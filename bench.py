@@ -344,7 +344,11 @@ def roofline_record(name, scene, counts, kern_ms, world, has_uv, info):
     rays, nodes, tris, hits, samples = counts
     alg = algorithmic_bytes(nodes, tris, hits, scene, has_uv)
     achieved = alg / world / (kern_ms * 1e-3) / 1e9          # per GPU: bytes one launch accounts for / its duration
-    cap = ncu_capture(name)
+    cap = dict(ncu_capture(name))
+    if cap.get("capture_spp") and cap.get("bytes"):
+        k = scene.spp / cap["capture_spp"]        # the capture rendered fewer samples per pixel than the frame: DRAM bytes and time scale with them
+        cap["bytes"] = int(cap["bytes"] * k); cap["captured_ms"] = cap.get("captured_ms", 0) * k
+        cap["capture"] = f'{cap.get("capture")} (captured at {cap["capture_spp"]} spp, bytes and time scaled x{k:g} to the {scene.spp}-spp frame)'
     rec = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "frac_is": "EFFECTIVE (cache-served): algorithmic bytes of SURVEY 8d / kernel time; the scene is L2-resident, see `secondary` for the real bound",
            "traffic": cap.get("bytes") if world == 1 else None, "peak_source": peak_src,

@@ -1,7 +1,8 @@
 """Reads .ncu-rep captures (no GPU needed) and writes the per-workload summary bench.py quotes (profiles/ncu_traffic.json):
 DRAM bytes per launch plus the counters that name the kernel's real bound.
 
-  python tools/ncu_to_json.py ajax-ao=gpurun_out/prof_r2_ajax-ao.ncu-rep cbox-mis=... [--note "build / config note"]
+  python tools/ncu_to_json.py ajax-ao=gpurun_out/prof_r2_ajax-ao.ncu-rep cbox-mis=prof.ncu-rep@64 [--note "build / config note"]
+(@N: the capture rendered N samples per pixel instead of the workload's full count)
 Each capture may hold several kernels (the wavefront engine: logic + trace); bytes and time are summed over the launches of
 ONE frame's worth named with --launches (default: the single longest launch), the ratios are those of the longest launch."""
 import csv
@@ -90,7 +91,12 @@ def main():
                     "that name its real bound, from ncu --set full captures (tools/ncu_to_json.py); bench.py copies them into roofline.traffic / roofline.secondary")
     for a in args:
         name, path = a.split("=", 1)
+        cap_spp = None
+        if "@" in path:
+            path, cap_spp = path.rsplit("@", 1); cap_spp = int(cap_spp)
         rec = summarise(path)
+        if cap_spp:
+            rec["capture_spp"] = cap_spp      # the capture rendered this many samples per pixel; bench.py scales bytes / time to the frame's
         if note:
             rec["note"] = note
         data[name] = rec
