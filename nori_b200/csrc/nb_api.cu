@@ -677,9 +677,9 @@ static int build_accel_local(nb_ctx *c) {
     const uint32_t bfs = c->opt_bfs_nodes < 0 ? nb::kSiblingPairs : (uint32_t) c->opt_bfs_nodes;
     // on-disk hierarchy cache (nb_set_accel_cache): keyed on every vertex / index the builder reads + the build parameters
     uint64_t key = 0; bool hit = false;
-    if (!c->accel_cache.empty()) { key = nb::bvh_cache_key(in, (int) c->opt_max_leaf, bfs, nb::kStack); hit = nb::bvh_cache_load(c->accel_cache.c_str(), key, out); }
+    if (!c->accel_cache.empty()) { key = nb::bvh_cache_key(in, (int) c->opt_max_leaf, bfs, nb::kStack, (int) c->opt_sah_bins); hit = nb::bvh_cache_load(c->accel_cache.c_str(), key, out); }
     if (!hit) {
-        nb::build_bvh(in, out, (int) c->opt_max_leaf, bfs, 0, nb::kStack);
+        nb::build_bvh(in, out, (int) c->opt_max_leaf, bfs, 0, nb::kStack, (int) c->opt_sah_bins);
         if (!c->accel_cache.empty()) nb::bvh_cache_save(c->accel_cache.c_str(), key, out);
     }
     c->accel_cache_hit = hit;
@@ -1165,6 +1165,7 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
         c->opt_max_leaf = value; c->built = false;
     }
     else if (k == "bfs_nodes") { c->opt_bfs_nodes = value; c->built = false; }
+    else if (k == "sah_bins") { if (value < 4 || value > 32) return fail("sah_bins must be in [4, 32]"); c->opt_sah_bins = value; c->built = false; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail("builder must be 0 (host SAH) or 1 (device LBVH)"); c->opt_builder = value; c->built = false; }
     else return fail("unknown option \"%s\"", key);
     for (nb_ctx *f : c->followers) if (nb_set_option(f, key, value)) return 1;

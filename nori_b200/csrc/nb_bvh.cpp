@@ -19,7 +19,7 @@
 namespace nb {
 namespace {
 
-constexpr int kBins = 16;
+constexpr int kBins = 32;           // array capacity; the number of bins in use is Builder::nbins (16 by default)
 constexpr float kInf = std::numeric_limits<float>::infinity();
 
 struct Box {
@@ -63,6 +63,7 @@ struct Builder {
     std::atomic<uint32_t> nnodes{0};
     std::atomic<int> threads_free{0};
     int max_leaf;
+    int nbins = 16;                  // SAH bins per axis (<= kBins)
     int max_depth = 64;              // the walk's per-lane stack: every leaf must end up shallower than this
 
     uint32_t alloc() { return nnodes.fetch_add(1); }
@@ -95,18 +96,19 @@ struct Builder {
         int lg = 0; while ((1u << lg) < n) ++lg;
         if (depth + 2 + lg < max_depth) {
             Box bins[3][kBins]; uint32_t cnt[3][kBins];
+            const int NB = nbins;
             float scale[3];
             for (int a = 0; a < 3; ++a) {
                 float ext = cbox.hi[a] - cbox.lo[a];
-                scale[a] = ext > 0 ? kBins / ext : 0.f;
-                for (int k = 0; k < kBins; ++k) { bins[a][k].reset(); cnt[a][k] = 0; }
+                scale[a] = ext > 0 ? NB / ext : 0.f;
+                for (int k = 0; k < NB; ++k) { bins[a][k].reset(); cnt[a][k] = 0; }
             }
             auto bin_range = [&](uint32_t b, uint32_t e, Box (*bn)[kBins], uint32_t (*cn)[kBins]) {
                 for (uint32_t i = b; i < e; ++i) {
                     const PrimRef &p = prims[order[i]];
                     for (int a = 0; a < 3; ++a) {
                         if (scale[a] == 0.f) continue;
-                        int k = std::min(kBins - 1, std::max(0, (int) ((p.c[a] - cbox.lo[a]) * scale[a])));
+                        int k = std::min(NB - 1, std::max(0, (int) ((p.c[a] - cbox.lo[a]) * scale[a])));
                         bn[a][k].grow(p.b); cn[a][k]++;
                     }
                 }
@@ -116,10 +118,10 @@ struct Builder {
                 std::vector<Part> parts((size_t) nthreads);
                 parallel_chunks(start, end, nthreads, [&](uint32_t b, uint32_t e, int c) {
                     Part &pt = parts[(size_t) c];
-                    for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k) { pt.b[a][k].reset(); pt.c[a][k] = 0; }
+                    for (int a = 0; a < 3; ++a) for (int k = 0; k < NB; ++k) { pt.b[a][k].reset(); pt.c[a][k] = 0; }
                     bin_range(b, e, pt.b, pt.c);
                 });
-                for (auto &pt : parts) for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k)
+                for (auto &pt : parts) for (int a = 0; a < 3; ++a) for (int k = 0; k < NB; ++k)
                     if (pt.c[a][k]) { bins[a][k].grow(pt.b[a][k]); cnt[a][k] += pt.c[a][k]; }
             } else {
                 bin_range(start, end, bins, cnt);
@@ -128,9 +130,9 @@ struct Builder {
                 if (scale[a] == 0.f) continue;
                 float ra[kBins]; uint32_t rc[kBins];
                 Box acc; acc.reset(); uint32_t c = 0;
-                for (int k = kBins - 1; k >= 0; --k) { if (cnt[a][k]) acc.grow(bins[a][k]); c += cnt[a][k]; ra[k] = acc.area(); rc[k] = c; }
+                for (int k = NB - 1; k >= 0; --k) { if (cnt[a][k]) acc.grow(bins[a][k]); c += cnt[a][k]; ra[k] = acc.area(); rc[k] = c; }
                 acc.reset(); c = 0;
-                for (int k = 0; k < kBins - 1; ++k) {
+                for (int k = 0; k < NB - 1; ++k) {
                     if (cnt[a][k]) acc.grow(bins[a][k]);
                     c += cnt[a][k];
                     if (c == 0 || rc[k + 1] == 0) continue;
@@ -144,9 +146,10 @@ struct Builder {
             mid = start + n / 2;
         } else {
             const int a = best_axis;
-            const float sc = kBins / (cbox.hi[a] - cbox.lo[a]), lo = cbox.lo[a];
+            const float sc = nbins / (cbox.hi[a] - cbox.lo[a]), lo = cbox.lo[a];
+            const int NBp = nbins;
             auto goes_left = [&](uint32_t id) {
-                int k = std::min(kBins - 1, std::max(0, (int) ((prims[id].c[a] - lo) * sc)));
+                int k = std::min(NBp - 1, std::max(0, (int) ((prims[id].c[a] - lo) * sc)));
                 return k <= best_bin;
             };
             if (wide && scratch) {
@@ -195,7 +198,7 @@ inline float as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 }  // namespace
 
-void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_nodes, int nthreads, int max_depth) {
+void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_nodes, int nthreads, int max_depth, int sah_bins) {
     auto t0 = std::chrono::steady_clock::now();
     max_leaf = std::min(8, std::max(1, max_leaf));
     const uint32_t n = in.nprims;
@@ -221,7 +224,7 @@ void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf, uint32_t bfs_no
 
     Builder b;
     std::vector<uint32_t> scratch(n >= Builder::kParallelNode ? n : 0);
-    b.prims = prims.data(); b.order = order.data(); b.max_leaf = max_leaf; b.max_depth = std::max(8, max_depth);
+    b.prims = prims.data(); b.order = order.data(); b.max_leaf = max_leaf; b.max_depth = std::max(8, max_depth); b.nbins = std::min(kBins, std::max(4, sah_bins));
     b.scratch = scratch.empty() ? nullptr : scratch.data();
     b.nodes.resize(n ? 2 * (size_t) n : 1);
     if (nthreads <= 0) nthreads = (int) std::thread::hardware_concurrency();
@@ -383,9 +386,9 @@ inline uint64_t fnv1a(const void *data, size_t n, uint64_t h) {
 }
 }  // namespace
 
-uint64_t bvh_cache_key(const BvhInput &in, int max_leaf, uint32_t bfs_nodes, int max_depth) {
+uint64_t bvh_cache_key(const BvhInput &in, int max_leaf, uint32_t bfs_nodes, int max_depth, int sah_bins) {
     uint64_t h = 0xcbf29ce484222325ull;
-    const uint32_t params[5] = { in.nprims, (uint32_t) max_leaf, bfs_nodes, 2u /* layout version */, (uint32_t) max_depth };
+    const uint32_t params[6] = { in.nprims, (uint32_t) max_leaf, bfs_nodes, 2u /* layout version */, (uint32_t) max_depth, (uint32_t) sah_bins };
     h = fnv1a(params, sizeof params, h);
     uint32_t max_v = 0;
     for (uint32_t i = 0; i < in.nprims; ++i) for (int k = 0; k < 3; ++k) max_v = std::max(max_v, in.faces[4 * (size_t) i + k]);

@@ -54,6 +54,15 @@ namespace nb {
 #define NB_STACK 64
 #endif
 constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
+#ifndef NB_PREFETCH_PUSH
+#define NB_PREFETCH_PUSH 0   // binary walk: prefetch.global.L1 of the far child's node when it is pushed (it is fetched at the pop)
+#endif
+#ifndef NB_PREFETCH_LEAF
+#define NB_PREFETCH_LEAF 0   // binary walk: prefetch.global.L1 of a leaf's first triangle when the leaf is parked (tested later)
+#endif
+#ifndef NB_STACK_SENTINEL
+#define NB_STACK_SENTINEL 0  // binary walk: stack[0] = kDone, pops without the emptiness test
+#endif
 #ifndef NB_WIDE
 #define NB_WIDE 0            // 1: the walk runs on the 8-wide compressed hierarchy (nb_wide.h) instead of the binary one
 #endif
@@ -63,7 +72,7 @@ constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders gu
 #if NB_WIDE
 typedef uint2 StackT; constexpr int kStackN = kWideStack;
 #else
-typedef int StackT; constexpr int kStackN = kStack;
+typedef int StackT; constexpr int kStackN = kStack + NB_STACK_SENTINEL;
 #endif
 constexpr int kBlockEdgeMax = 32 + 2 * 8;
 
@@ -289,6 +298,13 @@ template <bool COUNT, bool TMA_TOP>
 __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snodes, int smem_nodes, Ray &r, Trav &t,
                                          StackT *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris, int tail = 0) {
     int node = t.node, sp = t.sp;
+#if NB_STACK_SENTINEL
+    // the bottom slot holds kDone: a pop never has to ask whether the stack is empty (sp >= 1 whenever node is a real reference)
+    if (sp == 0) { stack[0] = kDone; sp = 1; }
+#define NB_POP() (stack[--sp])
+#else
+#define NB_POP() (sp ? stack[--sp] : kDone)
+#endif
     int parked = 0;                  // postponed leaf ref (leaf refs are negative; 0 = none)
     bool suspended = false;
 #if NB_SPECULATIVE >= 2
@@ -318,16 +334,25 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
             if (h0 && h1) {
                 const bool swap = c1min < c0min;
                 node = swap ? r1 : r0;
-                stack[sp++] = swap ? r0 : r1;
+                const int far_ref = swap ? r0 : r1;
+                stack[sp++] = far_ref;
+#if NB_PREFETCH_PUSH
+                if (far_ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.nodes + (size_t) far_ref * 4));
+#endif
             } else if (h0 || h1) {
                 node = h0 ? r0 : r1;
             } else {
-                node = sp ? stack[--sp] : kDone;
+                node = NB_POP();
             }
 #if NB_SPECULATIVE
-            if (node < 0 && parked == 0) { parked = node; node = sp ? stack[--sp] : kDone; }
+            if (node < 0 && parked == 0) {
+                parked = node; node = NB_POP();
+#if NB_PREFETCH_LEAF
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.tris + (size_t) ((~(unsigned) parked) >> 3) * 3));
+#endif
+            }
 #if NB_SPECULATIVE >= 2
-            if (node < 0 && parked2 == 0) { parked2 = node; node = sp ? stack[--sp] : kDone; }
+            if (node < 0 && parked2 == 0) { parked2 = node; node = NB_POP(); }
             if (__ballot_sync(__activemask(), parked2 == 0) == 0u) break;
 #elif NB_SPEC_VOTE
             if (__ballot_sync(__activemask(), parked == 0) == 0u) break;      // every lane still walking holds a leaf
@@ -346,11 +371,11 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
             parked2 = 0;
         }
 #endif
-        if (node < 0) { parked = node; node = sp ? stack[--sp] : kDone; }
+        if (node < 0) { parked = node; node = NB_POP(); }
 #else
         if (node == kDone) break;
         if (leaf_test<COUNT>(sc, node, r, t, any_hit, n_tris)) break;
-        node = sp ? stack[--sp] : kDone;
+        node = NB_POP();
 #endif
 #if NB_WAVEFRONT
         // ---- suspension (wavefront engine, nb_wave.cuh): when only a few lanes of the warp are still walking, they keep
@@ -364,6 +389,7 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
 #endif
     }
     if (suspended) { t.node = node; t.sp = sp; } else { t.node = kDone; t.sp = 0; }
+#undef NB_POP
 }
 #endif   // NB_WIDE
 
