@@ -41,13 +41,13 @@ struct BvhOutput {
 // the two inner children of a node share one aligned 128-byte line); nthreads <= 0: hardware concurrency
 constexpr uint32_t kSiblingPairs = 0xffffffffu;
 // max_depth: BvhOutput::depth is guaranteed to stay below it (the per-lane traversal stack of the kernels, nb::kStack)
-void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf = 4, uint32_t bfs_nodes = 2048, int nthreads = 0, int max_depth = 64, int sah_bins = 16);
+void build_bvh(const BvhInput &in, BvhOutput &out, int max_leaf = 4, uint32_t bfs_nodes = 2048, int nthreads = 0, int max_depth = 64, int sah_bins = 32);
 
 // ---- on-disk cache of the built hierarchy ("binary blob of V/N/UV/F + BVH"; the step the reference does
 // at every start, ref: src/obj.cpp:43-112 + Accel::build src/accel.cpp:19-21).  The key is a 64-bit FNV-1a hash over every
 // vertex and index the builder reads plus the build parameters and the layout version, so a stale or foreign file can only
 // miss.  File = header { magic, key, nnodes, ntris, top_nodes, depth, scene box } + nodes + leaf-ordered triangles.
-uint64_t bvh_cache_key(const BvhInput &in, int max_leaf, uint32_t bfs_nodes, int max_depth = 64, int sah_bins = 16);
+uint64_t bvh_cache_key(const BvhInput &in, int max_leaf, uint32_t bfs_nodes, int max_depth = 64, int sah_bins = 32);
 bool bvh_cache_load(const char *path, uint64_t key, BvhOutput &out);       // false: missing, unreadable, other key, truncated
 bool bvh_cache_save(const char *path, uint64_t key, const BvhOutput &out); // false: directory not writable (not an error)
 

@@ -82,7 +82,7 @@ struct nb_ctx {
     float4 *wf_cols = nullptr, *wf_shadow = nullptr; uint32_t *wf_ext = nullptr, *wf_ctr = nullptr, *wf_ctr_h = nullptr; size_t wf_cap = 0;
     int64_t opt_wf_pool = 1 << 21, opt_wf_check = 4;
     bool prog_active = false; uint32_t prog_done = 0, prog_pass = 0; nb_stats prog_stats = {};   // progressive frame (nb_render_begin .. nb_render_end)
-    int64_t opt_sah_bins = 16;         // SAH bins per axis of the host builder
+    int64_t opt_sah_bins = 32;         // SAH bins per axis of the host builder
     int64_t opt_prefetch = 0;          // L2 warm-up of nodes + triangles before the render kernel (l2_prefetch_kernel)
     int builder_used = 0;   // 0 host SAH, 1 device LBVH
     std::string accel_cache; bool accel_cache_hit = false;   // on-disk hierarchy cache (nb_set_accel_cache)

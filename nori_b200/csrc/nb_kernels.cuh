@@ -54,15 +54,6 @@ namespace nb {
 #define NB_STACK 64
 #endif
 constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
-#ifndef NB_PREFETCH_PUSH
-#define NB_PREFETCH_PUSH 0   // binary walk: prefetch.global.L1 of the far child's node when it is pushed (it is fetched at the pop)
-#endif
-#ifndef NB_PREFETCH_LEAF
-#define NB_PREFETCH_LEAF 0   // binary walk: prefetch.global.L1 of a leaf's first triangle when the leaf is parked (tested later)
-#endif
-#ifndef NB_STACK_SENTINEL
-#define NB_STACK_SENTINEL 0  // binary walk: stack[0] = kDone, pops without the emptiness test
-#endif
 #ifndef NB_WIDE
 #define NB_WIDE 0            // 1: the walk runs on the 8-wide compressed hierarchy (nb_wide.h) instead of the binary one
 #endif
@@ -72,7 +63,7 @@ constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders gu
 #if NB_WIDE
 typedef uint2 StackT; constexpr int kStackN = kWideStack;
 #else
-typedef int StackT; constexpr int kStackN = kStack + NB_STACK_SENTINEL;
+typedef int StackT; constexpr int kStackN = kStack;
 #endif
 constexpr int kBlockEdgeMax = 32 + 2 * 8;
 
@@ -298,13 +289,7 @@ template <bool COUNT, bool TMA_TOP>
 __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snodes, int smem_nodes, Ray &r, Trav &t,
                                          StackT *stack, bool any_hit, unsigned &n_nodes, unsigned &n_tris, int tail = 0) {
     int node = t.node, sp = t.sp;
-#if NB_STACK_SENTINEL
-    // the bottom slot holds kDone: a pop never has to ask whether the stack is empty (sp >= 1 whenever node is a real reference)
-    if (sp == 0) { stack[0] = kDone; sp = 1; }
-#define NB_POP() (stack[--sp])
-#else
 #define NB_POP() (sp ? stack[--sp] : kDone)
-#endif
     int parked = 0;                  // postponed leaf ref (leaf refs are negative; 0 = none)
     bool suspended = false;
 #if NB_SPECULATIVE >= 2
@@ -334,23 +319,14 @@ __device__ __forceinline__ void trav_run(const SceneDev &sc, const float4 *snode
             if (h0 && h1) {
                 const bool swap = c1min < c0min;
                 node = swap ? r1 : r0;
-                const int far_ref = swap ? r0 : r1;
-                stack[sp++] = far_ref;
-#if NB_PREFETCH_PUSH
-                if (far_ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.nodes + (size_t) far_ref * 4));
-#endif
+                stack[sp++] = swap ? r0 : r1;
             } else if (h0 || h1) {
                 node = h0 ? r0 : r1;
             } else {
                 node = NB_POP();
             }
 #if NB_SPECULATIVE
-            if (node < 0 && parked == 0) {
-                parked = node; node = NB_POP();
-#if NB_PREFETCH_LEAF
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.tris + (size_t) ((~(unsigned) parked) >> 3) * 3));
-#endif
-            }
+            if (node < 0 && parked == 0) { parked = node; node = NB_POP(); }
 #if NB_SPECULATIVE >= 2
             if (node < 0 && parked2 == 0) { parked2 = node; node = NB_POP(); }
             if (__ballot_sync(__activemask(), parked2 == 0) == 0u) break;
