@@ -442,7 +442,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h.info["bytes"]), "d2h_bytes_per_step": int(H2 * W2 * 16),
-                    "what": "nb_upload_scene (scene arrays from pinned host memory; N>1: PCIe once on rank 0, then ncclBroadcast over NVLink) + nb_render into a host film"},
+                    "what": "nb_upload_scene (the scene arena from pinned host memory; N>1: sharded, 1/N per rank over its own PCIe link + one in-place ncclAllGather over NVLink) + nb_render into a host film (N>1: nb_render_gather + film device->host on rank 0)"},
             "gpu_launches": int(args.steps * (world + 1)),   # per step: one render_kernel per rank + one merge kernel on rank 0
             "roofline": roofline_record(args.workload, scene, counts, float(np.mean(kern)), world, has_uv, h.info),
         }
