@@ -54,9 +54,6 @@ namespace nb {
 #define NB_STACK 64
 #endif
 constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
-#ifndef NB_SMEM_STATE
-#define NB_SMEM_STATE 0      // path integrators: the path state that is dead during the walk is parked in shared memory around it
-#endif                       // (instead of being spilled to local memory, which leaves L2 for DRAM: VERDICT r1 item 3)
 #ifndef NB_WIDE
 #define NB_WIDE 0            // 1: the walk runs on the 8-wide compressed hierarchy (nb_wide.h) instead of the binary one
 #endif
@@ -117,6 +114,7 @@ struct RenderParams {
     uint32_t *wf_ext;               // queue of pool slots whose extension ray waits to be traced
     uint32_t *wf_ctr;               // engine counters (nb_wave.cuh: WF_*)
     uint32_t wf_pool;               // path slots (multiple of 128)
+    uint32_t split_units, split_sample, chunk_a, nchunks_a;   // fused kernel, guided scheduling: coarse units first (samples [0, split_sample))
     uint32_t wf_chunk;              // samples per work unit (<= 8)
     unsigned long long wf_total;    // sample indices to hand out (virtual: ragged tiles / last chunk included)
 };
@@ -857,9 +855,6 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-#if NB_SMEM_STATE
-    __shared__ float park[16 * 128];
-#endif
 #if NB_SPLAT_TILE
     __shared__ float4 wtiles[4][kTileW * kTileH];
     float4 *wt = wtiles[threadIdx.x >> 5];
@@ -901,10 +896,15 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
                 // unit -> (owned tile, 8x4 patch, sample chunk); patches vary fastest
+                // Guided scheduling: the first split_units units are COARSE (chunk_a samples of a patch: a warp stays on its
+                // 32 pixels, the walk's nodes stay in L1), the rest FINE (chunk samples), so the frame ends on small units.
+                uint32_t chunk = P.chunk, nchunks = P.nchunks, sample0 = P.split_sample;
+                if (u < (unsigned long long) P.split_units) { chunk = P.chunk_a; nchunks = P.nchunks_a; sample0 = 0u; }
+                else u -= (unsigned long long) P.split_units;
                 const uint32_t patch = (uint32_t) (u % 32ULL);
                 const uint32_t rest = (uint32_t) (u / 32ULL);
-                const uint32_t chunk_id = rest % P.nchunks;
-                u_tile_slot = (int) (rest / P.nchunks);
+                const uint32_t chunk_id = rest % nchunks;
+                u_tile_slot = (int) (rest / nchunks);
                 const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;
                 const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
                 u_tox = bx * 32; u_toy = by * 32;
@@ -920,8 +920,8 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
                 const int lx = u_px0 + (int) (lane & 7u), ly = u_py0 + (int) (lane >> 3);
                 valid_mask = __ballot_sync(0xffffffffu, lx < P.W && ly < P.H);
                 n_valid = __popc(valid_mask);
-                sample_base = chunk_id * P.chunk;
-                const uint32_t ns = min(P.chunk, P.spp - sample_base);
+                sample_base = sample0 + chunk_id * chunk;
+                const uint32_t ns = min(chunk, P.spp - sample_base);
                 n_items = n_valid * ns; next_item = 0;
                 continue;
             }
@@ -951,31 +951,12 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
             const bool any_shadow = __ballot_sync(0xffffffffu, ps.stage >= ST_SHADOW) != 0u;
             traced = (any_shadow ? (ps.stage >= ST_SHADOW) : (ps.stage == ST_EXTEND));
         }
-#if NB_SMEM_STATE
-        // 16 words of path state are not touched by the walk: they wait in shared memory ([word][thread]: conflict free) instead of
-        // in registers the compiler would spill to local memory
-        if (INTEG >= 2) {
-            float *q = park + threadIdx.x;
-            q[0 * 128] = ps.L.x; q[1 * 128] = ps.L.y; q[2 * 128] = ps.L.z; q[3 * 128] = ps.T.x; q[4 * 128] = ps.T.y; q[5 * 128] = ps.T.z;
-            q[6 * 128] = ps.contrib.x; q[7 * 128] = ps.contrib.y; q[8 * 128] = ps.contrib.z;
-            q[9 * 128] = ps.next_d.x; q[10 * 128] = ps.next_d.y; q[11 * 128] = ps.next_d.z;
-            q[12 * 128] = ps.prev_pdf; q[13 * 128] = ps.sx; q[14 * 128] = ps.sy; q[15 * 128] = __int_as_float(ps.depth);
-        }
-#endif
         if (traced) {
             const WalkResult w = walk<COUNT, TMA_TOP>(P.sc.nodes, P.sc.tris, snodes, smem_nodes, ray.ox, ray.oy, ray.oz, ray.mint,
                                                       ray.dx, ray.dy, ray.dz, ray.maxt, ps.stage != ST_EXTEND);
             ray.maxt = w.t; tr.hu = w.u; tr.hv = w.v; tr.hprim = w.prim;
             if (COUNT) { n_nodes += w.n_nodes; n_tris += w.n_tris; wave_nodes = w.n_nodes; }
         }
-#if NB_SMEM_STATE
-        if (INTEG >= 2) {
-            const volatile float *q = park + threadIdx.x;       // volatile: the reload stays after the walk
-            ps.L = mk(q[0 * 128], q[1 * 128], q[2 * 128]); ps.T = mk(q[3 * 128], q[4 * 128], q[5 * 128]);
-            ps.contrib = mk(q[6 * 128], q[7 * 128], q[8 * 128]); ps.next_d = mk(q[9 * 128], q[10 * 128], q[11 * 128]);
-            ps.prev_pdf = q[12 * 128]; ps.sx = q[13 * 128]; ps.sy = q[14 * 128]; ps.depth = __float_as_int(q[15 * 128]);
-        }
-#endif
         if (COUNT) {
             // lock-step diagnostics: per wave, the longest walk (what the warp pays) vs the sum over lanes (what it needs)
             unsigned mx = wave_nodes;
