@@ -204,17 +204,36 @@ def test_instrumented_counts_match_plain(ctx):
     assert sa.rays == sb.rays and sb.node_visits > 0 and sb.tri_tests > 0 and S.rel_l2(a, b) < 1e-6
 
 
-@pytest.mark.parametrize("opt,val", [("smem_nodes", 512), ("chunk", 1), ("chunk", 64), ("blocks_per_sm", 1)])
+@pytest.mark.parametrize("opt,val", [("smem_nodes", 512), ("chunk", 1), ("chunk", 64), ("blocks_per_sm", 1), ("guided", 50), ("guided", 100),
+                                     ("prefetch", 1)])
 def test_tuning_options_do_not_change_results(ctx, oracle, opt, val):
-    sc = small_ajax(S.INT_AO, 4)
+    sc = small_ajax(S.INT_AO, 40 if opt == "guided" else 4)      # guided scheduling splits frames of >= 16 spp: 40 = 16 or 40 coarse + fine
     ctx.load(sc)
-    ref, _ = ctx.render()
+    ref, st0 = ctx.render()
     ctx.set_option(opt, val)
     try:
-        got, _ = ctx.render()
+        got, st = ctx.render()
     finally:
-        ctx.set_option(opt, {"smem_nodes": 0, "chunk": 0, "blocks_per_sm": 0}[opt])
-    assert S.rel_l2(got, ref) < 1e-6
+        ctx.set_option(opt, 0)
+    assert st.rays == st0.rays and S.rel_l2(got, ref) < 1e-6
+
+
+def test_sah_bin_count_changes_the_tree_not_the_image(ctx, oracle):
+    sc = small_ajax(S.INT_AO, 4, levels=3)
+    ctx.load(sc)
+    ref, st0 = ctx.render()
+    n0 = ctx.scene_info()["nodes"]
+    try:
+        for bins in (8, 16):
+            ctx.set_option("sah_bins", bins)
+            ctx.load(sc)
+            got, st = ctx.render()
+            assert st.rays == st0.rays and S.rel_l2(got, ref) < 1e-6
+        with pytest.raises(abi.NoriError, match="sah_bins"):
+            ctx.set_option("sah_bins", 64)
+    finally:
+        ctx.set_option("sah_bins", 32)
+    assert n0 > 0
 
 
 @pytest.mark.parametrize("integrator", ["whitted", "path_ems", "path_mats", "path_mis"])
