@@ -164,24 +164,18 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
         const int64_t units1 = (int64_t) P.n_my_tiles * 32 * spp;
         chunk = std::max<int64_t>(1, std::min<int64_t>(8, units1 / (16 * warps)));
     }
-    // Guided scheduling (option "guided" = percent of the samples rendered in coarse units of 8 samples per patch): the
-    // rest of the samples runs in fine units sized as above, so the frame ends on small units.
-    uint32_t split_sample = 0;
-    const uint32_t coarse = (uint32_t) std::max<int64_t>(2, std::min<int64_t>(16, c->opt_coarse));
-    if (c->opt_guided > 0 && c->opt_chunk <= 0 && spp >= 2 * coarse) split_sample = (uint32_t) ((uint64_t) spp * (uint64_t) std::min<int64_t>(c->opt_guided, 100) / 100 / coarse) * coarse;
-    if (split_sample) {
-        const int64_t warps = (int64_t) c->sm_count * NB_MIN_BLOCKS * 4;
-        const int64_t units_rest = (int64_t) P.n_my_tiles * 32 * (spp - split_sample);
-        chunk = std::max<int64_t>(1, std::min<int64_t>(8, units_rest / (16 * warps)));
+    // Guided self-scheduling (option "guided" = G > 0): the finest unit (chunk = 1 sample of a patch), sample chunks varying
+    // fastest, and a warp claims k = clamp(units left / (resident warps * G), 1, coarse) consecutive units per atomic.
+    P.guide_max = 0; P.guide_div = 1;
+    if (c->opt_guided > 0 && c->opt_chunk <= 0) {
+        chunk = 1;
+        P.guide_max = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(64, c->opt_coarse));
+        P.guide_div = (uint32_t) std::max<int64_t>(1, (int64_t) c->sm_count * NB_MIN_BLOCKS * 4 * c->opt_guided);
     }
-    const uint32_t spp_fine = spp - split_sample;
-    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, std::max<uint32_t>(spp_fine, 1u)));
-    P.nchunks = spp_fine ? (spp_fine + P.chunk - 1) / P.chunk : 0;
-    P.split_sample = split_sample; P.chunk_a = coarse; P.nchunks_a = split_sample / coarse;
-    const unsigned long long units_a = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks_a;
-    const unsigned long long units = units_a + (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
+    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, spp));
+    P.nchunks = (spp + P.chunk - 1) / P.chunk;
+    const unsigned long long units = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
     if (units > 0xffffffffULL) return fail("too many work units");
-    P.split_units = (uint32_t) units_a;
     P.n_units = (uint32_t) units;
     const size_t blk_elems = (size_t) P.n_my_tiles * P.block_edge * P.block_edge;
     if (!blocks_out) {
@@ -1167,8 +1161,8 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     }
     else if (k == "chunk") c->opt_chunk = value;
     else if (k == "count") c->opt_count = value;
-    else if (k == "coarse") { if (value != 0 && (value < 2 || value > 16)) return fail("coarse must be in [2, 16] (samples per coarse work unit)"); c->opt_coarse = value ? value : 8; }
-    else if (k == "guided") { if (value < 0 || value > 100) return fail("guided must be in [0, 100] (percent of the samples in coarse work units)"); c->opt_guided = value; }
+    else if (k == "coarse") { if (value != 0 && (value < 1 || value > 64)) return fail("coarse must be in [1, 64] (most units a warp claims at once)"); c->opt_coarse = value ? value : 8; }
+    else if (k == "guided") { if (value < 0 || value > 64) return fail("guided must be in [0, 64] (0: plain schedule; G: a warp claims units-left / (resident warps * G) units at a time)"); c->opt_guided = value; }
     else if (k == "prefetch") c->opt_prefetch = value;
     else if (k == "engine") { if (value != 0 && value != 2) return fail("engine must be 0 (fused kernel) or 2 (wavefront)"); c->opt_engine = value; }
     else if (k == "wf_pool") { if (value < 128 || value > (1ll << 28)) return fail("wf_pool must be in [128, 2^28]"); c->opt_wf_pool = value; }

@@ -83,8 +83,8 @@ struct nb_ctx {
     int64_t opt_wf_pool = 1 << 21, opt_wf_check = 4;
     bool prog_active = false; uint32_t prog_done = 0, prog_pass = 0; nb_stats prog_stats = {};   // progressive frame (nb_render_begin .. nb_render_end)
     int64_t opt_sah_bins = 32;         // SAH bins per axis of the host builder
-    int64_t opt_coarse = 8;            // samples per coarse work unit of the guided schedule
-    int64_t opt_guided = 0;            // fused kernel: percent of the samples scheduled in coarse (8-sample) work units
+    int64_t opt_coarse = 8;            // guided self-scheduling: most units (samples of a patch) a warp claims at once
+    int64_t opt_guided = 0;            // fused kernel: guided self-scheduling divisor G (0 = plain schedule)
     int64_t opt_prefetch = 0;          // L2 warm-up of nodes + triangles before the render kernel (l2_prefetch_kernel)
     int builder_used = 0;   // 0 host SAH, 1 device LBVH
     std::string accel_cache; bool accel_cache_hit = false;   // on-disk hierarchy cache (nb_set_accel_cache)

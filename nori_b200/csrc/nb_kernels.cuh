@@ -114,7 +114,7 @@ struct RenderParams {
     uint32_t *wf_ext;               // queue of pool slots whose extension ray waits to be traced
     uint32_t *wf_ctr;               // engine counters (nb_wave.cuh: WF_*)
     uint32_t wf_pool;               // path slots (multiple of 128)
-    uint32_t split_units, split_sample, chunk_a, nchunks_a;   // fused kernel, guided scheduling: coarse units first (samples [0, split_sample))
+    uint32_t guide_max, guide_div;  // fused kernel, guided self-scheduling: a warp claims min(guide_max, units left / guide_div) units at a time (0: one)
     uint32_t wf_chunk;              // samples per work unit (<= 8)
     unsigned long long wf_total;    // sample indices to hand out (virtual: ragged tiles / last chunk included)
 };
@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     // warp-uniform work-unit state
     bool exhausted = false, traced = false;
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
+    unsigned long long claim_next = 0, claim_end = 0;     // guided self-scheduling: the units this warp has claimed and not started
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
 
     for (;;) {
@@ -891,20 +892,40 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
         unsigned need_mask = __ballot_sync(0xffffffffu, need);
         while (need_mask != 0u && !exhausted) {
             if (next_item >= n_items) {
-                unsigned long long u = 0;
-                if (lane == 0) u = atomicAdd(&P.counters[0], 1ULL);
-                u = __shfl_sync(0xffffffffu, u, 0);
-                if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
-                // unit -> (owned tile, 8x4 patch, sample chunk); patches vary fastest
-                // Guided scheduling: the first split_units units are COARSE (chunk_a samples of a patch: a warp stays on its
-                // 32 pixels, the walk's nodes stay in L1), the rest FINE (chunk samples), so the frame ends on small units.
-                uint32_t chunk = P.chunk, nchunks = P.nchunks, sample0 = P.split_sample;
-                if (u < (unsigned long long) P.split_units) { chunk = P.chunk_a; nchunks = P.nchunks_a; sample0 = 0u; }
-                else u -= (unsigned long long) P.split_units;
-                const uint32_t patch = (uint32_t) (u % 32ULL);
-                const uint32_t rest = (uint32_t) (u / 32ULL);
-                const uint32_t chunk_id = rest % nchunks;
-                u_tile_slot = (int) (rest / nchunks);
+                // A unit = (owned tile, 8x4 pixel patch, chunk of P.chunk samples).
+                // Plain schedule (guide_max == 0): one unit per atomic, patches varying fastest.
+                // Guided self-scheduling (guide_max > 0): sample chunks vary fastest and a warp CLAIMS k consecutive units per
+                // atomic, k = clamp(units left / guide_div, 1, guide_max) -- many samples of one patch while the frame is young (the
+                // warp stays on its 32 pixels, its walks share their nodes in L1), single units near the end (no tail).
+                unsigned long long u;
+                uint32_t span = 1;                 // consecutive units of ONE patch taken now
+                if (P.guide_max == 0u) {
+                    u = 0;
+                    if (lane == 0) u = atomicAdd(&P.counters[0], 1ULL);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
+                } else {
+                    if (claim_next >= claim_end) {
+                        unsigned long long c0 = 0; unsigned k = 1;
+                        if (lane == 0) {
+                            const unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(&P.counters[0]);
+                            const unsigned long long left = seen < (unsigned long long) P.n_units ? (unsigned long long) P.n_units - seen : 0ULL;
+                            k = (unsigned) min((unsigned long long) P.guide_max, max(left / (unsigned long long) P.guide_div, 1ULL));
+                            c0 = atomicAdd(&P.counters[0], (unsigned long long) k);
+                        }
+                        c0 = __shfl_sync(0xffffffffu, c0, 0); k = __shfl_sync(0xffffffffu, k, 0);
+                        if (c0 >= (unsigned long long) P.n_units) { exhausted = true; break; }
+                        claim_next = c0; claim_end = min(c0 + (unsigned long long) k, (unsigned long long) P.n_units);
+                    }
+                    u = claim_next;
+                    span = (uint32_t) min(claim_end - claim_next, (unsigned long long) (P.nchunks - (uint32_t) (u % (unsigned long long) P.nchunks)));   // up to the patch's last chunk
+                    claim_next += span;
+                }
+                const uint32_t chunk = P.chunk, nchunks = P.nchunks, sample0 = 0u;
+                uint32_t patch, chunk_id, rest;
+                if (P.guide_max == 0u) { patch = (uint32_t) (u % 32ULL); rest = (uint32_t) (u / 32ULL); chunk_id = rest % nchunks; rest = rest / nchunks; }
+                else { chunk_id = (uint32_t) (u % (unsigned long long) nchunks); rest = (uint32_t) (u / (unsigned long long) nchunks); patch = rest % 32u; rest = rest / 32u; }
+                u_tile_slot = (int) rest;
                 const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;
                 const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
                 u_tox = bx * 32; u_toy = by * 32;
@@ -921,7 +942,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
                 valid_mask = __ballot_sync(0xffffffffu, lx < P.W && ly < P.H);
                 n_valid = __popc(valid_mask);
                 sample_base = sample0 + chunk_id * chunk;
-                const uint32_t ns = min(chunk, P.spp - sample_base);
+                const uint32_t ns = min(span * chunk, P.spp - sample_base);
                 n_items = n_valid * ns; next_item = 0;
                 continue;
             }

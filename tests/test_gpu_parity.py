@@ -204,10 +204,10 @@ def test_instrumented_counts_match_plain(ctx):
     assert sa.rays == sb.rays and sb.node_visits > 0 and sb.tri_tests > 0 and S.rel_l2(a, b) < 1e-6
 
 
-@pytest.mark.parametrize("opt,val", [("smem_nodes", 512), ("chunk", 1), ("chunk", 64), ("blocks_per_sm", 1), ("guided", 50), ("guided", 100),
+@pytest.mark.parametrize("opt,val", [("smem_nodes", 512), ("chunk", 1), ("chunk", 64), ("blocks_per_sm", 1), ("guided", 1), ("guided", 4),
                                      ("prefetch", 1)])
 def test_tuning_options_do_not_change_results(ctx, oracle, opt, val):
-    sc = small_ajax(S.INT_AO, 40 if opt == "guided" else 4)      # guided scheduling splits frames of >= 16 spp: 40 = 16 or 40 coarse + fine
+    sc = small_ajax(S.INT_AO, 13 if opt == "guided" else 4, 170, 123)   # guided self-scheduling: claims of several sample units, ragged tiles, 13 spp
     ctx.load(sc)
     ref, st0 = ctx.render()
     ctx.set_option(opt, val)
