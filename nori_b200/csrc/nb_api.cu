@@ -7,6 +7,7 @@
 #include "nb_kernels.cuh"
 #include "nb_lbvh.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -44,6 +45,39 @@ int tiles_for(const nb_ctx *c, int rank, int nranks, int *ntx_out, int *nty_out)
 }
 
 int ensure_device(nb_ctx *c) { CK(cudaSetDevice(c->device)); return 0; }
+
+// Numbering of the image's 32x32 tiles for a group of `nranks` GPUs: tile_tab[t] = bx | by << 16 (nb_kernels.cuh: tile_xy), GPU
+// t % nranks owns tile t.  Ownership follows the Latin pattern (bx + shift * by) % nranks, shift = 3 (5 or 7 when 3 divides nranks) -- every row and every column of tiles
+// deals its tiles evenly to all ranks, the pattern with the lowest load imbalance on the BASELINE frames among row-major,
+// diagonal, Z-order and hashed assignments -- and rank r's k-th tile (row by row) is tile k * nranks + r.
+// The few tiles by which the pattern misses the counts the numbering implies (rank r owns ceil((total - r) / nranks) tiles)
+// move from the ranks with a surplus (their last tiles) to the ranks with a deficit.  oracle.c and multigpu.py build the same.
+void build_tile_order(int ntx, int nty, int nranks, std::vector<uint32_t> &tab) {
+    const int total = ntx * nty;
+    const int shift = nranks % 3 ? 3 : nranks % 5 ? 5 : 7;      // coprime to the group size (groups of up to 16): no rank owns a column
+    std::vector<std::vector<uint32_t>> lists((size_t) nranks);
+    for (int by = 0; by < nty; ++by) for (int bx = 0; bx < ntx; ++bx) lists[(size_t) ((bx + shift * by) % nranks)].push_back((uint32_t) bx | ((uint32_t) by << 16));
+    std::vector<uint32_t> pool;
+    auto target = [&](int r) { return total > r ? (size_t) ((total - r + nranks - 1) / nranks) : (size_t) 0; };
+    for (int r = 0; r < nranks; ++r) while (lists[(size_t) r].size() > target(r)) { pool.push_back(lists[(size_t) r].back()); lists[(size_t) r].pop_back(); }
+    size_t head = 0;
+    for (int r = 0; r < nranks; ++r) while (lists[(size_t) r].size() < target(r)) lists[(size_t) r].push_back(pool[head++]);
+    tab.assign((size_t) total, 0u);
+    for (int r = 0; r < nranks; ++r) for (size_t q = 0; q < lists[(size_t) r].size(); ++q) tab[q * (size_t) nranks + (size_t) r] = lists[(size_t) r][q];
+}
+
+int ensure_tile_table(nb_ctx *c, int nranks) {
+    if (c->tile_tab_d && c->tab_W == c->W && c->tab_H == c->H && c->tab_N == nranks) return 0;
+    const int ntx = (c->W + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE, nty = (c->H + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE;
+    build_tile_order(ntx, nty, nranks, c->tile_tab_h);
+    if (c->tile_tab_d) cudaFree(c->tile_tab_d);
+    c->tile_tab_d = nullptr;
+    CK(cudaMalloc(&c->tile_tab_d, sizeof(uint32_t) * std::max<size_t>(c->tile_tab_h.size(), 1)));
+    CK(cudaMemcpyAsync(c->tile_tab_d, c->tile_tab_h.data(), sizeof(uint32_t) * c->tile_tab_h.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->tab_W = c->W; c->tab_H = c->H; c->tab_N = nranks;
+    return 0;
+}
 
 int fill_scene(nb_ctx *c, nb::SceneDev &sc) {
     if (!c->built) return fail("nb_build_accel has not been called");
@@ -154,28 +188,38 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
     P.tile_rank = c->tile_rank; P.tile_nranks = c->tile_nranks;
     P.n_my_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, &P.ntx, &P.nty);
+    if (ensure_tile_table(c, c->tile_nranks)) return 1;
+    P.tile_tab = c->tile_tab_d;
     P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
     if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
-    // samples per work unit: explicit option, else as coarse as 8 while leaving >= 16 units per resident warp
-    // (few tiles per GPU at N = 8 would otherwise quantise the tail: 2.6 units per warp at chunk 8)
+    // Work units = (owned tile, 8x4 pixel patch, chunk of samples).  Chunk 8 renders 11 % faster than chunk 1 (a warp stays on its
+    // 32 pixels, its walks share their nodes in L1) but a frame must END on small units, and a unit must stay a small part of
+    // the frame (profiles/r2_call7_work_unit_size.txt, r2_call8_static_guided_ab.txt).  GUIDED schedule: the first `guided` percent
+    // of the samples go in COARSE units -- the largest power of two <= 8 that still leaves >= 12 coarse units per resident warp
+    // -- the rest in FINE units sized to leave >= 16 per warp.  Small shares (8 GPUs on the 9 ms frame) degenerate to the plain
+    // fine schedule.  An explicit `chunk` option switches the schedule off.
+    const int64_t warps = (int64_t) c->sm_count * NB_MIN_BLOCKS * 4;
     int64_t chunk = c->opt_chunk;
+    uint32_t split_sample = 0, coarse = 1;
     if (chunk <= 0) {
-        const int64_t warps = (int64_t) c->sm_count * NB_MIN_BLOCKS * 4;
-        const int64_t units1 = (int64_t) P.n_my_tiles * 32 * spp;
-        chunk = std::max<int64_t>(1, std::min<int64_t>(8, units1 / (16 * warps)));
+        const int64_t guided = std::max<int64_t>(0, std::min<int64_t>(100, c->opt_guided));
+        const int64_t want = c->opt_coarse > 0 ? c->opt_coarse : 8;
+        for (int64_t cc = want; cc >= 2 && !split_sample; cc /= 2) {
+            const uint32_t ss = (uint32_t) ((uint64_t) spp * (uint64_t) guided / 100 / (uint64_t) cc) * (uint32_t) cc;
+            if (ss >= (uint32_t) cc && (int64_t) P.n_my_tiles * 32 * (ss / cc) >= 12 * warps) { split_sample = ss; coarse = (uint32_t) cc; }
+        }
+        const int64_t units_fine = (int64_t) P.n_my_tiles * 32 * (spp - split_sample);
+        chunk = std::max<int64_t>(1, std::min<int64_t>(8, units_fine / (16 * warps)));
+        if (split_sample && chunk >= (int64_t) coarse) { split_sample = 0; chunk = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t) P.n_my_tiles * 32 * spp / (16 * warps))); }
     }
-    // Guided self-scheduling (option "guided" = G > 0): the finest unit (chunk = 1 sample of a patch), sample chunks varying
-    // fastest, and a warp claims k = clamp(units left / (resident warps * G), 1, coarse) consecutive units per atomic.
-    P.guide_max = 0; P.guide_div = 1;
-    if (c->opt_guided > 0 && c->opt_chunk <= 0) {
-        chunk = 1;
-        P.guide_max = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(64, c->opt_coarse));
-        P.guide_div = (uint32_t) std::max<int64_t>(1, (int64_t) c->sm_count * NB_MIN_BLOCKS * 4 * c->opt_guided);
-    }
-    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, spp));
-    P.nchunks = (spp + P.chunk - 1) / P.chunk;
-    const unsigned long long units = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
+    const uint32_t spp_fine = spp - split_sample;
+    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t) std::max<uint32_t>(spp_fine, 1u)));
+    P.nchunks = spp_fine ? (spp_fine + P.chunk - 1) / P.chunk : 0;
+    P.split_sample = split_sample; P.chunk_a = coarse; P.nchunks_a = split_sample / coarse;
+    const unsigned long long units_a = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks_a;
+    const unsigned long long units = units_a + (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
     if (units > 0xffffffffULL) return fail("too many work units");
+    P.split_units = (uint32_t) units_a;
     P.n_units = (uint32_t) units;
     const size_t blk_elems = (size_t) P.n_my_tiles * P.block_edge * P.block_edge;
     if (!blocks_out) {
@@ -241,7 +285,7 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
         // samples rendered by this context
         unsigned long long ns = 0;
         for (int k = 0; k < P.n_my_tiles; ++k) {
-            int tile_id = c->tile_rank + k * c->tile_nranks, bx = tile_id % P.ntx, by = tile_id / P.ntx;
+            const uint32_t tv = c->tile_tab_h[(size_t) (c->tile_rank + k * c->tile_nranks)]; const int bx = (int) (tv & 0xffffu), by = (int) (tv >> 16);
             ns += (unsigned long long) std::min(32, c->W - bx * 32) * std::min(32, c->H - by * 32);
         }
         st->samples = ns * spp;
@@ -281,6 +325,8 @@ int render_blocks_wave(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *
     P.max_depth = c->integ.max_depth > 0 ? c->integ.max_depth : (1 << 20);
     P.tile_rank = c->tile_rank; P.tile_nranks = c->tile_nranks;
     P.n_my_tiles = tiles_for(c, c->tile_rank, c->tile_nranks, &P.ntx, &P.nty);
+    if (ensure_tile_table(c, c->tile_nranks)) return 1;
+    P.tile_tab = c->tile_tab_d;
     P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
     if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
     P.wf_chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(c->opt_chunk > 0 ? c->opt_chunk : 8, std::min<int64_t>(8, spp)));
@@ -357,7 +403,7 @@ int render_blocks_wave(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *
         memset(st, 0, sizeof *st);
         unsigned long long ns = 0;
         for (int k = 0; k < P.n_my_tiles; ++k) {
-            int tile_id = c->tile_rank + k * c->tile_nranks, bx = tile_id % P.ntx, by = tile_id / P.ntx;
+            const uint32_t tv = c->tile_tab_h[(size_t) (c->tile_rank + k * c->tile_nranks)]; const int bx = (int) (tv & 0xffffu), by = (int) (tv >> 16);
             ns += (unsigned long long) std::min(32, c->W - bx * 32) * std::min(32, c->H - by * 32);
         }
         st->samples = ns * spp;
@@ -377,7 +423,8 @@ int merge(nb_ctx *c, const float4 *blocks, int n_tiles, int rank, int nranks, fl
     int edge = NB_BLOCK_SIZE + 2 * c->border;
     long long total = (long long) n_tiles * edge * edge;
     int grid = (int) ((total + 255) / 256);
-    nb::merge_blocks_kernel<<<grid, 256, 0, s>>>(blocks, n_tiles, rank, nranks, ntx, c->W, c->H, c->border, edge, film);
+    if (ensure_tile_table(c, nranks)) return 1;
+    nb::merge_blocks_kernel<<<grid, 256, 0, s>>>(blocks, n_tiles, rank, nranks, c->tile_tab_d, c->W, c->H, c->border, edge, film);
     CK(cudaGetLastError());
     return 0;
 }
@@ -498,6 +545,7 @@ void nb_destroy(nb_ctx *c) {
     cudaSetDevice(c->device);
     nbm::release_group(c);
     arena_release(c);
+    if (c->tile_tab_d) cudaFree(c->tile_tab_d);
     if (c->shard_h) cudaFreeHost(c->shard_h);
     if (c->blocks) cudaFree(c->blocks);
     if (c->film) cudaFree(c->film);
@@ -823,8 +871,9 @@ int nb_merge_all_blocks_device(nb_ctx *c, const float *blocks_dev, int nranks, i
     const int edge = NB_BLOCK_SIZE + 2 * c->border;
     const long long total = (long long) nranks * stride_tiles * edge * edge;
     if (total == 0) return 0;
+    if (ensure_tile_table(c, nranks)) return 1;
     nb::merge_all_blocks_kernel<<<(int) ((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(blocks_dev), nranks, stride_tiles,
-                                                                           ntx * nty, ntx, c->W, c->H, c->border, edge, reinterpret_cast<float4 *>(film_dev));
+                                                                           ntx * nty, c->tile_tab_d, c->W, c->H, c->border, edge, reinterpret_cast<float4 *>(film_dev));
     CK(cudaGetLastError());
     return 0;
 }
@@ -1161,8 +1210,8 @@ int nb_set_option(nb_ctx *c, const char *key, int64_t value) {
     }
     else if (k == "chunk") c->opt_chunk = value;
     else if (k == "count") c->opt_count = value;
-    else if (k == "coarse") { if (value != 0 && (value < 1 || value > 64)) return fail("coarse must be in [1, 64] (most units a warp claims at once)"); c->opt_coarse = value ? value : 8; }
-    else if (k == "guided") { if (value < 0 || value > 64) return fail("guided must be in [0, 64] (0: plain schedule; G: a warp claims units-left / (resident warps * G) units at a time)"); c->opt_guided = value; }
+    else if (k == "coarse") { if (value != 0 && value != 2 && value != 4 && value != 8 && value != 16) return fail("coarse must be 2, 4, 8 or 16 (samples per coarse work unit; 0 = default 8)"); c->opt_coarse = value ? value : 8; }
+    else if (k == "guided") { if (value < -1 || value > 100) return fail("guided must be in [0, 100] (percent of the samples in coarse work units; -1 = default 75)"); c->opt_guided = value < 0 ? 75 : value; }
     else if (k == "prefetch") c->opt_prefetch = value;
     else if (k == "engine") { if (value != 0 && value != 2) return fail("engine must be 0 (fused kernel) or 2 (wavefront)"); c->opt_engine = value; }
     else if (k == "wf_pool") { if (value < 128 || value > (1ll << 28)) return fail("wf_pool must be in [128, 2^28]"); c->opt_wf_pool = value; }

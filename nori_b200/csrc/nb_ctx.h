@@ -70,6 +70,7 @@ struct nb_ctx {
     nb_integrator_desc integ = { NB_INT_NORMALS, 3, 0, 0 };
     float light_pos[3] = { 0, 0, 0 }, light_energy[3] = { 0, 0, 0 }; bool have_light = false;
     int tile_rank = 0, tile_nranks = 1;
+    std::vector<uint32_t> tile_tab_h; uint32_t *tile_tab_d = nullptr; int tab_W = 0, tab_H = 0, tab_N = 0;   // tile numbering for tab_N ranks (ensure_tile_table)
     // work buffers
     float4 *blocks = nullptr; size_t blocks_cap = 0;
     float4 *film = nullptr; size_t film_cap = 0; bool film_valid = false;   // film_valid: holds the last nb_render's film
@@ -83,8 +84,8 @@ struct nb_ctx {
     int64_t opt_wf_pool = 1 << 21, opt_wf_check = 4;
     bool prog_active = false; uint32_t prog_done = 0, prog_pass = 0; nb_stats prog_stats = {};   // progressive frame (nb_render_begin .. nb_render_end)
     int64_t opt_sah_bins = 32;         // SAH bins per axis of the host builder
-    int64_t opt_coarse = 8;            // guided self-scheduling: most units (samples of a patch) a warp claims at once
-    int64_t opt_guided = 0;            // fused kernel: guided self-scheduling divisor G (0 = plain schedule)
+    int64_t opt_coarse = 8;            // guided schedule: samples per coarse work unit (upper bound)
+    int64_t opt_guided = 75;           // fused kernel: percent of the samples scheduled in coarse work units (0 = plain schedule)
     int64_t opt_prefetch = 0;          // L2 warm-up of nodes + triangles before the render kernel (l2_prefetch_kernel)
     int builder_used = 0;   // 0 host SAH, 1 device LBVH
     std::string accel_cache; bool accel_cache_hit = false;   // on-disk hierarchy cache (nb_set_accel_cache)

@@ -67,6 +67,16 @@ typedef int StackT; constexpr int kStackN = kStack;
 #endif
 constexpr int kBlockEdgeMax = 32 + 2 * 8;
 
+// Tile t of the image's grid of 32x32 tiles (ref: BlockGenerator, src/block.cpp:109-152; the order is cosmetic there).  GPU
+// t % N owns tile t; the numbering comes from a table the host builds for N ranks (nb_api.cu: build_tile_order; entry = bx | by << 16)
+// so that ownership follows the Latin pattern (bx + 3 * by) % N: every row and column of tiles is dealt evenly to all GPUs.
+// Row-major numbering hands whole COLUMNS of tiles to a GPU when N divides the row length (768 / 32 = 24 tiles on 8 GPUs: the
+// ranks holding the object's columns ran 15 % longer, profiles/r2_call8_static_guided_ab.txt).
+__device__ __forceinline__ void tile_xy(const uint32_t *tab, int t, int &bx, int &by) {
+    const uint32_t v = __ldg(&tab[t]);
+    bx = (int) (v & 0xffffu); by = (int) (v >> 16);
+}
+
 struct SceneDev {
     const float4 *nodes;            // 4 x float4 per node
     const float4 *tris;             // 3 x float4 per leaf-ordered triangle
@@ -114,7 +124,8 @@ struct RenderParams {
     uint32_t *wf_ext;               // queue of pool slots whose extension ray waits to be traced
     uint32_t *wf_ctr;               // engine counters (nb_wave.cuh: WF_*)
     uint32_t wf_pool;               // path slots (multiple of 128)
-    uint32_t guide_max, guide_div;  // fused kernel, guided self-scheduling: a warp claims min(guide_max, units left / guide_div) units at a time (0: one)
+    const uint32_t *tile_tab;       // tile t -> bx | by << 16, Z-order numbering (tile_xy)
+    uint32_t split_units, split_sample, chunk_a, nchunks_a;   // fused kernel, guided schedule: coarse units first (samples [0, split_sample))
     uint32_t wf_chunk;              // samples per work unit (<= 8)
     unsigned long long wf_total;    // sample indices to hand out (virtual: ragged tiles / last chunk included)
 };
@@ -514,7 +525,8 @@ struct WarpTile { int slot, px0, py0; bool valid; };      // warp-uniform: owned
 __device__ __forceinline__ void tile_flush(const RenderParams &P, float4 *wt, WarpTile &T, unsigned lane) {
     if (T.valid) {
         const int tile_id = P.tile_rank + T.slot * P.tile_nranks;
-        const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+        int tbx, tby; tile_xy(P.tile_tab, tile_id, tbx, tby);
+        const int tox = tbx * 32, toy = tby * 32;
         float4 *blk = P.blocks + (size_t) T.slot * P.block_edge * P.block_edge;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -538,7 +550,8 @@ __device__ __forceinline__ bool splat_tile(const RenderParams &P, float4 *wt, co
     if (!T.valid || P.border != 2 || tile_slot != T.slot || px < T.px0 || px >= T.px0 + 8 || py < T.py0 || py >= T.py0 + 4) return false;
     if (value.x < 0 || !isfinite(value.x) || value.y < 0 || !isfinite(value.y) || value.z < 0 || !isfinite(value.z)) return true;
     const int tile_id = P.tile_rank + tile_slot * P.tile_nranks;
-    const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+    int tbx, tby; tile_xy(P.tile_tab, tile_id, tbx, tby);
+    const int tox = tbx * 32, toy = tby * 32;
     const float posx = sx - 0.5f - (float) (tox - 2), posy = sy - 0.5f - (float) (toy - 2);       // block coordinates, as in splat()
     int x0 = (int) ceilf(posx - P.fradius), y0 = (int) ceilf(posy - P.fradius);
     int x1 = (int) floorf(posx + P.fradius), y1 = (int) floorf(posy + P.fradius);
@@ -870,7 +883,6 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     // warp-uniform work-unit state
     bool exhausted = false, traced = false;
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
-    unsigned long long claim_next = 0, claim_end = 0;     // guided self-scheduling: the units this warp has claimed and not started
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
 
     for (;;) {
@@ -892,42 +904,22 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
         unsigned need_mask = __ballot_sync(0xffffffffu, need);
         while (need_mask != 0u && !exhausted) {
             if (next_item >= n_items) {
-                // A unit = (owned tile, 8x4 pixel patch, chunk of P.chunk samples).
-                // Plain schedule (guide_max == 0): one unit per atomic, patches varying fastest.
-                // Guided self-scheduling (guide_max > 0): sample chunks vary fastest and a warp CLAIMS k consecutive units per
-                // atomic, k = clamp(units left / guide_div, 1, guide_max) -- many samples of one patch while the frame is young (the
-                // warp stays on its 32 pixels, its walks share their nodes in L1), single units near the end (no tail).
-                unsigned long long u;
-                uint32_t span = 1;                 // consecutive units of ONE patch taken now
-                if (P.guide_max == 0u) {
-                    u = 0;
-                    if (lane == 0) u = atomicAdd(&P.counters[0], 1ULL);
-                    u = __shfl_sync(0xffffffffu, u, 0);
-                    if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
-                } else {
-                    if (claim_next >= claim_end) {
-                        unsigned long long c0 = 0; unsigned k = 1;
-                        if (lane == 0) {
-                            const unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(&P.counters[0]);
-                            const unsigned long long left = seen < (unsigned long long) P.n_units ? (unsigned long long) P.n_units - seen : 0ULL;
-                            k = (unsigned) min((unsigned long long) P.guide_max, max(left / (unsigned long long) P.guide_div, 1ULL));
-                            c0 = atomicAdd(&P.counters[0], (unsigned long long) k);
-                        }
-                        c0 = __shfl_sync(0xffffffffu, c0, 0); k = __shfl_sync(0xffffffffu, k, 0);
-                        if (c0 >= (unsigned long long) P.n_units) { exhausted = true; break; }
-                        claim_next = c0; claim_end = min(c0 + (unsigned long long) k, (unsigned long long) P.n_units);
-                    }
-                    u = claim_next;
-                    span = (uint32_t) min(claim_end - claim_next, (unsigned long long) (P.nchunks - (uint32_t) (u % (unsigned long long) P.nchunks)));   // up to the patch's last chunk
-                    claim_next += span;
-                }
-                const uint32_t chunk = P.chunk, nchunks = P.nchunks, sample0 = 0u;
-                uint32_t patch, chunk_id, rest;
-                if (P.guide_max == 0u) { patch = (uint32_t) (u % 32ULL); rest = (uint32_t) (u / 32ULL); chunk_id = rest % nchunks; rest = rest / nchunks; }
-                else { chunk_id = (uint32_t) (u % (unsigned long long) nchunks); rest = (uint32_t) (u / (unsigned long long) nchunks); patch = rest % 32u; rest = rest / 32u; }
-                u_tile_slot = (int) rest;
+                unsigned long long u = 0;
+                if (lane == 0) u = atomicAdd(&P.counters[0], 1ULL);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
+                // unit -> (owned tile, 8x4 patch, sample chunk); patches vary fastest (concurrent warps splat into different pixels).
+                // Guided schedule: the first split_units units are COARSE (chunk_a samples of a patch: the warp stays on its 32
+                // pixels and its walks share their nodes in L1), the rest FINE (chunk samples): the frame ends on small units.
+                uint32_t chunk = P.chunk, nchunks = P.nchunks, sample0 = P.split_sample;
+                if (u < (unsigned long long) P.split_units) { chunk = P.chunk_a; nchunks = P.nchunks_a; sample0 = 0u; }
+                else u -= (unsigned long long) P.split_units;
+                const uint32_t patch = (uint32_t) (u % 32ULL);
+                const uint32_t rest = (uint32_t) (u / 32ULL);
+                const uint32_t chunk_id = rest % nchunks;
+                u_tile_slot = (int) (rest / nchunks);
                 const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;
-                const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
+                int bx, by; tile_xy(P.tile_tab, tile_id, bx, by);
                 u_tox = bx * 32; u_toy = by * 32;
                 u_tsx = min(32, P.W - u_tox); u_tsy = min(32, P.H - u_toy);
                 u_px0 = u_tox + (int) (patch & 3u) * 8; u_py0 = u_toy + (int) (patch >> 2) * 4;
@@ -942,7 +934,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
                 valid_mask = __ballot_sync(0xffffffffu, lx < P.W && ly < P.H);
                 n_valid = __popc(valid_mask);
                 sample_base = sample0 + chunk_id * chunk;
-                const uint32_t ns = min(span * chunk, P.spp - sample_base);
+                const uint32_t ns = min(chunk, P.spp - sample_base);
                 n_items = n_valid * ns; next_item = 0;
                 continue;
             }
@@ -1015,7 +1007,7 @@ __global__ void __launch_bounds__(32) render_block_mode_kernel(const __grid_cons
     Path ps; Ray ray; Trav tr;
     unsigned n_rays = 0, n_nodes = 0, n_tris = 0, n_hits = 0;
     const int tile_id = P.tile_rank + slot * P.tile_nranks;
-    const int bx = tile_id % P.ntx, by = tile_id / P.ntx;
+    int bx, by; tile_xy(P.tile_tab, tile_id, bx, by);
     const int tox = bx * 32, toy = by * 32, tsx = min(32, P.W - tox), tsy = min(32, P.H - toy);
     pcg_seed(ps.rng, (uint64_t) tox, (uint64_t) toy);
     ps.tile_slot = slot; ps.tox = (short) tox; ps.toy = (short) toy; ps.tsx = (unsigned char) tsx; ps.tsy = (unsigned char) tsy;
@@ -1066,7 +1058,7 @@ __global__ void __launch_bounds__(128) li_samples_kernel(const __grid_constant__
 
 
 // ------------------------------------------------------------------ K6: merge finished blocks into the full film (ref: src/block.cpp:93-102)
-__global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank, int nranks, int ntx, int W, int H,
+__global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank, int nranks, const uint32_t *tile_tab, int W, int H,
                                     int border, int block_edge, float4 *film) {
     const int per_block = block_edge * block_edge;
     const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -1074,7 +1066,7 @@ __global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank,
     const int slot = (int) (gid / per_block), r = (int) (gid % per_block);
     const int y = r / block_edge, x = r % block_edge;
     const int tile_id = rank + slot * nranks;
-    const int bx = tile_id % ntx, by = tile_id / ntx;
+    int bx, by; tile_xy(tile_tab, tile_id, bx, by);
     const int tox = bx * 32, toy = by * 32;
     const int tsx = min(32, W - tox), tsy = min(32, H - toy);
     if (x >= tsx + 2 * border || y >= tsy + 2 * border) return;
@@ -1086,7 +1078,7 @@ __global__ void merge_blocks_kernel(const float4 *blocks, int n_tiles, int rank,
 
 // Same merge for the gathered blocks of ALL ranks in one launch: blocks = [nranks][stride_tiles][edge][edge] (ranks
 // padded to stride_tiles); slot k of rank r is tile r + k * nranks.
-__global__ void merge_all_blocks_kernel(const float4 *blocks, int nranks, int stride_tiles, int total_tiles, int ntx, int W, int H,
+__global__ void merge_all_blocks_kernel(const float4 *blocks, int nranks, int stride_tiles, int total_tiles, const uint32_t *tile_tab, int W, int H,
                                         int border, int block_edge, float4 *film) {
     const int per_block = block_edge * block_edge;
     const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -1097,7 +1089,7 @@ __global__ void merge_all_blocks_kernel(const float4 *blocks, int nranks, int st
     const int tile_id = rank + slot * nranks;
     if (tile_id >= total_tiles) return;
     const int y = r / block_edge, x = r % block_edge;
-    const int bx = tile_id % ntx, by = tile_id / ntx;
+    int bx, by; tile_xy(tile_tab, tile_id, bx, by);
     const int tox = bx * 32, toy = by * 32;
     const int tsx = min(32, W - tox), tsy = min(32, H - toy);
     if (x >= tsx + 2 * border || y >= tsy + 2 * border) return;

@@ -242,7 +242,8 @@ int render_group(nb_ctx *c, float4 *film, cudaStream_t s0, nb_stats *st) {
         CK(cudaMemsetAsync(film, 0, sizeof(float4) * film_elems, s));
         const long long total = (long long) nranks * n_max * edge * edge;
         if (total) {
-            nb::merge_all_blocks_kernel<<<(int) ((total + 255) / 256), 256, 0, s>>>(x->gather, nranks, n_max, ntx * nty, ntx, x->W, x->H, x->border, edge, film);
+            if (ensure_tile_table(x, nranks)) return 1;
+            nb::merge_all_blocks_kernel<<<(int) ((total + 255) / 256), 256, 0, s>>>(x->gather, nranks, n_max, ntx * nty, x->tile_tab_d, x->W, x->H, x->border, edge, film);
             CK(cudaGetLastError());
         }
     }

@@ -50,7 +50,8 @@ __device__ __forceinline__ bool wf_decode(const RenderParams &P, unsigned long l
     const uint32_t chunk_id = (uint32_t) (rest % P.nchunks);
     tile_slot = (int) (rest / P.nchunks);
     const int tile_id = P.tile_rank + tile_slot * P.tile_nranks;
-    const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+    int tbx, tby; tile_xy(P.tile_tab, tile_id, tbx, tby);
+    const int tox = tbx * 32, toy = tby * 32;
     const uint32_t pl = item & 31u;
     px = tox + (int) (patch & 3u) * 8 + (int) (pl & 7u);
     py = toy + (int) (patch >> 2) * 4 + (int) (pl >> 3);
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__(128, 4) wf_logic_kernel(const __grid_constant_
     }
     if (done) {
         const int tile_id = P.tile_rank + ps.tile_slot * P.tile_nranks;
-        const int tox = (tile_id % P.ntx) * 32, toy = (tile_id / P.ntx) * 32;
+        int tbx, tby; tile_xy(P.tile_tab, tile_id, tbx, tby);
+    const int tox = tbx * 32, toy = tby * 32;
         splat(P, ps.tile_slot, tox, toy, min(32, P.W - tox), min(32, P.H - toy), ps.sx, ps.sy, ps.L);
         stage = WST_EMPTY;
     }

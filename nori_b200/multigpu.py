@@ -17,12 +17,38 @@ def tile_grid(W: int, H: int):
     return (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
 
 
+def tile_order(W: int, H: int, world: int):
+    """[(bx, by)] in the tile numbering of the device path for `world` ranks (nb_api.cu: build_tile_order): rank t % world owns tile t,
+    ownership follows the Latin pattern (bx + shift * by) % world (shift 3; 5 or 7 when 3 divides world), rank r's k-th tile (row by row) is tile k * world + r; the few tiles by
+    which the pattern misses the implied counts move from the ranks with a surplus (their last tiles) to those with a deficit."""
+    ntx, nty = tile_grid(W, H)
+    total = ntx * nty
+    lists = [[] for _ in range(world)]
+    shift = 3 if world % 3 else 5 if world % 5 else 7
+    for by in range(nty):
+        for bx in range(ntx):
+            lists[(bx + shift * by) % world].append((bx, by))
+    target = [(total - r + world - 1) // world if total > r else 0 for r in range(world)]
+    pool = []
+    for r in range(world):
+        while len(lists[r]) > target[r]:
+            pool.append(lists[r].pop())
+    for r in range(world):
+        while len(lists[r]) < target[r]:
+            lists[r].append(pool.pop(0))
+    order = [None] * total
+    for r in range(world):
+        for k, t in enumerate(lists[r]):
+            order[k * world + r] = t
+    return order
+
+
 def tiles_of(rank: int, world: int, W: int, H: int):
     """[(tile_id, ox, oy, sx, sy)] owned by `rank`, in the packed-block order of nb_render_blocks_device."""
-    ntx, nty = tile_grid(W, H)
+    order = tile_order(W, H, world)
     out = []
-    for tid in range(rank, ntx * nty, world):
-        bx, by = tid % ntx, tid // ntx
+    for tid in range(rank, len(order), world):
+        bx, by = order[tid]
         ox, oy = bx * BLOCK, by * BLOCK
         out.append((tid, ox, oy, min(BLOCK, W - ox), min(BLOCK, H - oy)))
     return out

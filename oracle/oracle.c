@@ -1051,6 +1051,24 @@ int orc_render(orc_scene *s, float *film, int accel, int nthreads, orc_stats *st
     int32_t *order = (int32_t *) malloc(sizeof(int32_t) * 2 * ntiles);
     orc_block_order(W, H, ORC_BLOCK, order);
     block_t *blocks = (block_t *) calloc(ntiles, sizeof(block_t));
+    /* Tile shards (multi-GPU slices): tile t is owned by rank t % nranks.  Numbering of the device path (nb_api.cu:
+     * build_tile_order): ownership follows the Latin pattern (bx + shift by) % nranks (shift = 3; 5 or 7 when 3 divides nranks), rank r's k-th tile (row by row) is tile
+     * k * nranks + r; the few tiles by which the pattern misses the implied counts move from the ranks with a surplus (their last
+     * tiles) to those with a deficit.  zrank[by * nbx + bx] = t */
+    int32_t *zrank = (int32_t *) malloc(sizeof(int32_t) * ntiles);
+    {
+        const int N = s->tile_nranks;
+        int32_t *lists = (int32_t *) malloc(sizeof(int32_t) * (size_t) N * ntiles);     /* lists[r * ntiles + k] = cell */
+        int32_t *len = (int32_t *) calloc((size_t) N, sizeof(int32_t));
+        int32_t *pool = (int32_t *) malloc(sizeof(int32_t) * ntiles);
+        int npool = 0, head = 0;
+        const int shift = N % 3 ? 3 : N % 5 ? 5 : 7;
+        for (int y = 0; y < nby; ++y) for (int x = 0; x < nbx; ++x) { int r = (x + shift * y) % N; lists[(size_t) r * ntiles + len[r]++] = y * nbx + x; }
+        for (int r = 0; r < N; ++r) { int target = ntiles > r ? (ntiles - r + N - 1) / N : 0; while (len[r] > target) pool[npool++] = lists[(size_t) r * ntiles + --len[r]]; }
+        for (int r = 0; r < N; ++r) { int target = ntiles > r ? (ntiles - r + N - 1) / N : 0; while (len[r] < target) lists[(size_t) r * ntiles + len[r]++] = pool[head++]; }
+        for (int r = 0; r < N; ++r) for (int k = 0; k < len[r]; ++k) zrank[lists[(size_t) r * ntiles + k]] = k * N + r;
+        free(lists); free(len); free(pool);
+    }
     uint64_t nsamples = 0;
     for (int i = 0; i < ntiles; ++i) {
         block_t *b = &blocks[i];
@@ -1059,12 +1077,13 @@ int orc_render(orc_scene *s, float *film, int accel, int nthreads, orc_stats *st
         b->sx = W - b->ox < ORC_BLOCK ? W - b->ox : ORC_BLOCK;   /* ref: src/block.cpp:129 */
         b->sy = H - b->oy < ORC_BLOCK ? H - b->oy : ORC_BLOCK;
         b->border = bd; b->cols = b->sx + 2 * bd; b->rows = b->sy + 2 * bd;
-        int tile_id = by * nbx + bx;
+        int tile_id = zrank[by * nbx + bx];   /* tile numbering of the device path */
         if (tile_id % s->tile_nranks == s->tile_rank) {
             b->px = (float *) malloc(sizeof(float) * 4 * (size_t) b->rows * b->cols);
             nsamples += (uint64_t) b->sx * b->sy * s->spp;
         }
     }
+    free(zrank);
     pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
     job_t job; memset(&job, 0, sizeof job);
     job.s = s; job.accel = accel; job.ntiles = ntiles; job.order = order; job.blocks = blocks; job.mu = &mu;

@@ -51,10 +51,11 @@ def test_tile_shard_gather_merge(tmp_path, world, W, H, border):
     # expected: single-rank assembly of the same synthetic blocks
     n1 = MG.max_tiles(1, W, H)
     all_blocks = np.zeros((n1, 32 + 2 * border, 32 + 2 * border, 4), np.float32)
+    where1 = {(ox, oy): tid for tid, ox, oy, _, _ in MG.tiles_of(0, 1, W, H)}     # the numbering depends on the group size: go through the tile origin
     for r in range(world):
         b = _synthetic_blocks(r, world, W, H, border, MG.max_tiles(world, W, H))
-        for k, (tid, *_rest) in enumerate(MG.tiles_of(r, world, W, H)):
-            all_blocks[tid] = b[k]
+        for k, (tid, ox, oy, _, _) in enumerate(MG.tiles_of(r, world, W, H)):
+            all_blocks[where1[(ox, oy)]] = b[k]
     expect = MG.merge_blocks_numpy([all_blocks], W, H, border)
     assert np.allclose(film, expect, rtol=1e-6, atol=1e-6)
 
@@ -72,3 +73,7 @@ def test_tiles_partition_the_image():
             assert np.all(seen == 1) and sorted(ids) == list(range(len(ids)))
             counts = [len(MG.tiles_of(r, world, W, H)) for r in range(world)]
             assert max(counts) - min(counts) <= 1
+            # ownership follows the Latin pattern (bx + shift by) % world except for the few tiles moved to even out the counts
+            shift = 3 if world % 3 else 5
+            off = sum(1 for r in range(world) for _, ox, oy, _, _ in MG.tiles_of(r, world, W, H) if (ox // 32 + shift * (oy // 32)) % world != r)
+            assert off <= 2 * world
