@@ -218,7 +218,7 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     P.split_sample = split_sample; P.chunk_a = coarse; P.nchunks_a = split_sample / coarse;
     const unsigned long long units_a = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks_a;
     const unsigned long long units = units_a + (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
-    if (units > 0xffffffffULL) return fail("too many work units");
+    if (units > 0xf0000000ULL) return fail("too many work units");      // (+ one claim per warp past the end stays below 2^32)
     P.split_units = (uint32_t) units_a;
     P.n_units = (uint32_t) units;
     const size_t blk_elems = (size_t) P.n_my_tiles * P.block_edge * P.block_edge;

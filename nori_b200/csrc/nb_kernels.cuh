@@ -53,6 +53,9 @@ namespace nb {
 #ifndef NB_STACK
 #define NB_STACK 64
 #endif
+#ifndef NB_UNIT_AHEAD
+#define NB_UNIT_AHEAD 0      // 1: a warp claims its next work unit one fetch ahead (hides the atomic's round trip)
+#endif
 constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
 #ifndef NB_WIDE
 #define NB_WIDE 0            // 1: the walk runs on the 8-wide compressed hierarchy (nb_wide.h) instead of the binary one
@@ -884,6 +887,10 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     bool exhausted = false, traced = false;
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
+#if NB_UNIT_AHEAD
+    uint32_t u_ahead = 0;
+    if (lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
+#endif
 
     for (;;) {
         // ---- shading phase (lock step: every lane's ray is finished here)
@@ -904,18 +911,26 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
         unsigned need_mask = __ballot_sync(0xffffffffu, need);
         while (need_mask != 0u && !exhausted) {
             if (next_item >= n_items) {
-                unsigned long long u = 0;
-                if (lane == 0) u = atomicAdd(&P.counters[0], 1ULL);
+#if NB_UNIT_AHEAD
+                // lane 0 holds the index of a unit claimed one fetch ahead: the atomic's round trip (~1 us: the longest
+                // dependent latency of a wave of short rays) overlaps the previous unit's work instead of stalling the warp
+                uint32_t u = __shfl_sync(0xffffffffu, u_ahead, 0);      // (n_units + one claim per warp < 2^32: render_blocks)
+                if (u >= P.n_units) { exhausted = true; break; }
+                if (lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
+#else
+                uint32_t u = 0;
+                if (lane == 0) u = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
                 u = __shfl_sync(0xffffffffu, u, 0);
-                if (u >= (unsigned long long) P.n_units) { exhausted = true; break; }
+                if (u >= P.n_units) { exhausted = true; break; }
+#endif
                 // unit -> (owned tile, 8x4 patch, sample chunk); patches vary fastest (concurrent warps splat into different pixels).
                 // Guided schedule: the first split_units units are COARSE (chunk_a samples of a patch: the warp stays on its 32
                 // pixels and its walks share their nodes in L1), the rest FINE (chunk samples): the frame ends on small units.
                 uint32_t chunk = P.chunk, nchunks = P.nchunks, sample0 = P.split_sample;
-                if (u < (unsigned long long) P.split_units) { chunk = P.chunk_a; nchunks = P.nchunks_a; sample0 = 0u; }
-                else u -= (unsigned long long) P.split_units;
-                const uint32_t patch = (uint32_t) (u % 32ULL);
-                const uint32_t rest = (uint32_t) (u / 32ULL);
+                if (u < P.split_units) { chunk = P.chunk_a; nchunks = P.nchunks_a; sample0 = 0u; }
+                else u -= P.split_units;
+                const uint32_t patch = u % 32u;
+                const uint32_t rest = u / 32u;
                 const uint32_t chunk_id = rest % nchunks;
                 u_tile_slot = (int) (rest / nchunks);
                 const int tile_id = P.tile_rank + u_tile_slot * P.tile_nranks;

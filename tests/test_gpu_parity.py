@@ -219,22 +219,22 @@ def test_tuning_options_do_not_change_results(ctx, oracle, opt, val):
 
 def test_guided_schedule_does_not_change_results(ctx, oracle):
     """The default schedule splits a frame's samples into coarse work units (first `guided` percent) and fine ones (the rest)
-    once there are >= 12 coarse units per resident warp (nb_api.cu: render_blocks); small frames never get there, so this one
-    has enough samples per pixel: ragged tiles, an odd sample count, every coarse size."""
-    sc = small_ajax(S.INT_AO, 83, 170, 123)
+    once there are >= 12 coarse units per resident warp (nb_api.cu: render_blocks: 71 040 on a B200); the small frames of the
+    other tests never get there, so this one has 4 160 patches x 197 samples: ragged tiles, an odd sample count, every coarse size."""
+    sc = small_ajax(S.INT_AO, 197, 400, 300)
     ctx.load(sc)
-    got, st = ctx.render()                                   # default: guided 75, coarse 2 at this size
+    got, st = ctx.render()                                   # default: guided 75, coarse 8 at this size
     ofilm, ost = oracle.OracleScene(sc).render(accel=1)
     assert st.rays == ost.rays and S.rel_l2(got, ofilm) <= 1e-4
-    sc = small_ajax(S.INT_AO, 601, 170, 123)
-    ctx.load(sc)
     try:
         ctx.set_option("guided", 0)                          # one unit size for the whole frame
         ref, st0 = ctx.render()
-        for guided, coarse in [(75, 8), (100, 8), (40, 4), (75, 16), (1, 2)]:
+        assert st0.rays == ost.rays and S.rel_l2(ref, ofilm) <= 1e-4
+        for guided, coarse in [(100, 8), (40, 4), (75, 2), (75, 16), (1, 2)]:
             ctx.set_option("guided", guided); ctx.set_option("coarse", coarse)
             got, st = ctx.render()
-            assert st.rays == st0.rays and S.rel_l2(got, ref) < 1e-6, (guided, coarse)
+            assert st.rays == st0.rays, (guided, coarse)
+            assert S.rel_l2(got, ref) < 1e-5, (guided, coarse, S.rel_l2(got, ref))      # 197 float atomics per pixel land in another order
     finally:
         ctx.set_option("guided", -1); ctx.set_option("coarse", 8)
 

@@ -35,5 +35,5 @@ for spec in optsets:
     print(f"SHARD {wl} N={N} [{spec}] kernel ms: max over ranks {max(per_rank):.4f}  mean {np.mean(per_rank):.4f}  per rank {[round(x, 3) for x in per_rank]}", flush=True)
     for kv in spec.split(","):          # back to defaults
         k, v = kv.split("=")
-        ctx.set_option(k, 0)
+        ctx.set_option(k, -1 if k == "guided" else 0)
 ctx.close()
