@@ -54,7 +54,7 @@ namespace nb {
 #define NB_STACK 64
 #endif
 #ifndef NB_UNIT_AHEAD
-#define NB_UNIT_AHEAD 0      // 1: a warp claims its next work unit one fetch ahead (hides the atomic's round trip)
+#define NB_UNIT_AHEAD 0      // 1: a warp claims its next work unit one wave before it runs out of items (hides the atomic's round trip)
 #endif
 constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
 #ifndef NB_WIDE
@@ -888,8 +888,7 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
 #if NB_UNIT_AHEAD
-    uint32_t u_ahead = 0;
-    if (lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
+    uint32_t u_ahead = 0; bool ahead = false;
 #endif
 
     for (;;) {
@@ -912,11 +911,12 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
         while (need_mask != 0u && !exhausted) {
             if (next_item >= n_items) {
 #if NB_UNIT_AHEAD
-                // lane 0 holds the index of a unit claimed one fetch ahead: the atomic's round trip (~1 us: the longest
-                // dependent latency of a wave of short rays) overlaps the previous unit's work instead of stalling the warp
+                // lane 0 may hold the index of a unit claimed when the previous one was down to its last wave of items (below):
+                // the atomic's round trip then overlapped that wave instead of stalling this one
+                if (!ahead && lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
                 uint32_t u = __shfl_sync(0xffffffffu, u_ahead, 0);      // (n_units + one claim per warp < 2^32: render_blocks)
+                ahead = false;
                 if (u >= P.n_units) { exhausted = true; break; }
-                if (lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
 #else
                 uint32_t u = 0;
                 if (lane == 0) u = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
@@ -968,6 +968,11 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
             }
             next_item += min((uint32_t) __popc(need_mask), avail);
             need_mask = __ballot_sync(0xffffffffu, need);
+#if NB_UNIT_AHEAD
+            // claim the next unit when this one is down to one wave of items: early enough to hide the atomic's latency, late
+            // enough that concurrently claimed units stay neighbours (claiming a whole unit ahead measured slower: profiles/r2_call11)
+            if (!ahead && n_items - next_item <= 32u) { if (lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL); ahead = true; }
+#endif
         }
         if (__ballot_sync(0xffffffffu, ps.stage != ST_IDLE) == 0u) break;     // work exhausted and every path retired
         // ---- traversal phase: every active lane walks its ray to completion.  Path integrators run PHASED waves
