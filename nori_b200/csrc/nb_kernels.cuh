@@ -53,9 +53,6 @@ namespace nb {
 #ifndef NB_STACK
 #define NB_STACK 64
 #endif
-#ifndef NB_UNIT_AHEAD
-#define NB_UNIT_AHEAD 0      // 1: a warp claims its next work unit one wave before it runs out of items (hides the atomic's round trip)
-#endif
 constexpr int kStack = NB_STACK;    // per-lane traversal stack; the builders guarantee depth < kStack (nb_bvh.cpp, nb_lbvh.cuh)
 #ifndef NB_WIDE
 #define NB_WIDE 0            // 1: the walk runs on the 8-wide compressed hierarchy (nb_wide.h) instead of the binary one
@@ -887,9 +884,6 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
     bool exhausted = false, traced = false;
     uint32_t next_item = 0, n_items = 0, valid_mask = 0, n_valid = 0, sample_base = 0;
     int u_tile_slot = 0, u_tox = 0, u_toy = 0, u_tsx = 0, u_tsy = 0, u_px0 = 0, u_py0 = 0;
-#if NB_UNIT_AHEAD
-    uint32_t u_ahead = 0; bool ahead = false;
-#endif
 
     for (;;) {
         // ---- shading phase (lock step: every lane's ray is finished here)
@@ -910,19 +904,10 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
         unsigned need_mask = __ballot_sync(0xffffffffu, need);
         while (need_mask != 0u && !exhausted) {
             if (next_item >= n_items) {
-#if NB_UNIT_AHEAD
-                // lane 0 may hold the index of a unit claimed when the previous one was down to its last wave of items (below):
-                // the atomic's round trip then overlapped that wave instead of stalling this one
-                if (!ahead && lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
-                uint32_t u = __shfl_sync(0xffffffffu, u_ahead, 0);      // (n_units + one claim per warp < 2^32: render_blocks)
-                ahead = false;
-                if (u >= P.n_units) { exhausted = true; break; }
-#else
                 uint32_t u = 0;
                 if (lane == 0) u = (uint32_t) atomicAdd(&P.counters[0], 1ULL);
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= P.n_units) { exhausted = true; break; }
-#endif
                 // unit -> (owned tile, 8x4 patch, sample chunk); patches vary fastest (concurrent warps splat into different pixels).
                 // Guided schedule: the first split_units units are COARSE (chunk_a samples of a patch: the warp stays on its 32
                 // pixels and its walks share their nodes in L1), the rest FINE (chunk samples): the frame ends on small units.
@@ -968,11 +953,6 @@ __global__ void __launch_bounds__(128, (INTEG <= 1 || INTEG == 6) ? NB_MIN_BLOCK
             }
             next_item += min((uint32_t) __popc(need_mask), avail);
             need_mask = __ballot_sync(0xffffffffu, need);
-#if NB_UNIT_AHEAD
-            // claim the next unit when this one is down to one wave of items: early enough to hide the atomic's latency, late
-            // enough that concurrently claimed units stay neighbours (claiming a whole unit ahead measured slower: profiles/r2_call11)
-            if (!ahead && n_items - next_item <= 32u) { if (lane == 0) u_ahead = (uint32_t) atomicAdd(&P.counters[0], 1ULL); ahead = true; }
-#endif
         }
         if (__ballot_sync(0xffffffffu, ps.stage != ST_IDLE) == 0u) break;     // work exhausted and every path retired
         // ---- traversal phase: every active lane walks its ray to completion.  Path integrators run PHASED waves
