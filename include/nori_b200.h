@@ -169,7 +169,7 @@ int nb_bsdf_sample(nb_ctx *, const nb_bsdf_desc *, const float *wi, int wi_per_q
 int nb_bsdf_eval_pdf(nb_ctx *, const nb_bsdf_desc *, const float *wi, int wi_per_query, const float *wo, uint64_t n, float *out4);
 
 /* Tile sharding across GPUs: this context renders only 32x32 tiles with tile_id % nranks == rank
- * (the numbering depends on nranks: ownership follows the Latin pattern (bx + 3 * by) % nranks over the ceil(W/32) x ceil(H/32) tile grid -- every row and column of tiles is dealt evenly to all ranks -- and rank r's k-th tile, row by row, is tile k * nranks + r).  Default (0, 1) = all tiles.  Replaces BlockGenerator::next
+ * (the numbering depends on nranks: ownership follows the Latin pattern (bx + shift * by) % nranks, shift = 3 -- 5 or 7 when 3 divides nranks --, over the ceil(W/32) x ceil(H/32) tile grid -- every row and column of tiles is dealt evenly to all ranks -- and rank r's k-th tile, row by row, is tile k * nranks + r).  Default (0, 1) = all tiles.  Replaces BlockGenerator::next
  * as the work scheduler (ref: src/block.cpp:119-152). */
 int nb_set_tiles(nb_ctx *, int rank, int nranks);
 
