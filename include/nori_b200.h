@@ -239,6 +239,9 @@ int nb_debug_counters(nb_ctx *, uint64_t out[8]);
  * outputs to size the arrays (capacities in floats).  Returns 0, 1 (bad argument) or 2 (capacity too small). */
 int nb_debug_build_bvh(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes,
                        float *nodes_out, uint64_t nodes_cap, float *tris_out, uint64_t tris_cap, uint32_t info[4]);
+/* Host-only diagnostic of the tile numbering (no context, no device): out[t] = bx | by << 16 of tile t for a group of
+ * `nranks` (see nb_set_tiles); ceil(width/32) * ceil(height/32) entries.  Returns 0, 1 (bad argument) or 2 (capacity). */
+int nb_debug_tile_order(int width, int height, int nranks, uint32_t *bx_by_out, uint64_t cap);
 /* Host-only diagnostic of the hierarchy cache: key -> load, else build + save, exactly as nb_build_accel does with
  * nb_set_accel_cache.  info = { nodes, leaf triangles, top nodes, depth, hit (0/1) }. */
 int nb_debug_bvh_cache(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes, const char *path,

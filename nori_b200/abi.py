@@ -80,6 +80,7 @@ def lib():
         L.nb_accel_cache_hit.argtypes = [vp]
         L.nb_debug_build_wide.argtypes = [vp, vp, u32, vp, u64, vp, u64, vp]
         L.nb_debug_wide_intersect.argtypes = [vp, u32, vp, vp, u64, i, vp, vp]
+        L.nb_debug_tile_order.argtypes = [i, i, i, vp, u64]
         L.nb_debug_bvh_cache.argtypes = [vp, vp, u32, i, C.c_int64, C.c_char_p, vp, u64, vp, u64, vp]
         L.nb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i)]
         L.nb_set_camera.argtypes = [vp, vp, vp, i, i, f, f]
@@ -166,6 +167,17 @@ def debug_wide_intersect(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, 
     if rc:
         raise NoriError(f"nb_debug_wide_intersect failed ({rc})")
     return out, counts
+
+
+def debug_tile_order(width, height, nranks):
+    """nb_debug_tile_order (no GPU): [(bx, by)] in the device path's tile numbering for a group of `nranks`."""
+    L = lib()
+    n = ((width + 31) // 32) * ((height + 31) // 32)
+    out = np.zeros(n, dtype=np.uint32)
+    rc = L.nb_debug_tile_order(width, height, nranks, _p(out), out.size)
+    if rc != 0:
+        raise NoriError(f"nb_debug_tile_order failed ({rc})")
+    return [(int(v & 0xffff), int(v >> 16)) for v in out]
 
 
 def debug_bvh_cache(V: np.ndarray, F: np.ndarray, path: str, max_leaf=3, bfs_nodes=2048):

@@ -842,6 +842,18 @@ int nb_tile_count(nb_ctx *c, int rank, int nranks, int *ntiles, int *block_edge)
     return 0;
 }
 
+// Host-only diagnostic (no context, no device): the tile numbering nb_set_tiles / nb_render use for a group of `nranks`.
+int nb_debug_tile_order(int width, int height, int nranks, uint32_t *bx_by_out, uint64_t cap) {
+    if (width < 1 || height < 1 || nranks < 1) return 1;
+    const int ntx = (width + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE, nty = (height + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE;
+    if (!bx_by_out) return 0;
+    if (cap < (uint64_t) ntx * (uint64_t) nty) return 2;
+    std::vector<uint32_t> tab;
+    build_tile_order(ntx, nty, nranks, tab);
+    for (size_t i = 0; i < tab.size(); ++i) bx_by_out[i] = tab[i];
+    return 0;
+}
+
 int nb_render_blocks_device(nb_ctx *c, float *blocks_dev, void *stream, nb_stats *st) {
     if (!c || !blocks_dev) return fail("null argument");
     cudaStream_t s = stream ? (cudaStream_t) stream : c->stream;

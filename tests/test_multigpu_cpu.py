@@ -77,3 +77,39 @@ def test_tiles_partition_the_image():
             shift = 3 if world % 3 else 5
             off = sum(1 for r in range(world) for _, ox, oy, _, _ in MG.tiles_of(r, world, W, H) if (ox // 32 + shift * (oy // 32)) % world != r)
             assert off <= 2 * world
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 6, 8])
+def test_oracle_shards_follow_the_same_tile_table(oracle, world):
+    """The device path (nb_api.cu: build_tile_order), the oracle (oracle.c: orc_render) and this package (multigpu.tile_order)
+    each build the group-size dependent tile numbering; the GPU tests compare the first with the other two, this one pins the
+    last two against each other on the CPU: rank r's oracle frame has filter weight at the centre of exactly the tiles
+    tiles_of(r, world) lists, and the ranks' frames add up to the unsharded frame."""
+    from nori_b200 import scene as S
+    W, H = 296, 200                                         # 10 x 7 tiles, ragged on both edges
+    sc = S.Scene([S.ajax_standin(1)], S.Camera(S.lookat(**S._AJAX_CAM).astype(np.float32), 30.0, W, H), S.INT_NORMALS, 1)
+    b = sc.border
+    full, _ = oracle.OracleScene(sc).render(accel=1)
+    total = np.zeros_like(full)
+    for r in range(world):
+        o = oracle.OracleScene(sc)
+        o.set_tiles(r, world)
+        part, st = o.render(accel=1)
+        total += part
+        mine = {(ox, oy) for _, ox, oy, _, _ in MG.tiles_of(r, world, W, H)}
+        assert st.samples == sum(sx * sy for _, _, _, sx, sy in MG.tiles_of(r, world, W, H))
+        for _, ox, oy, sx, sy in MG.tiles_of(0, 1, W, H):
+            if sx < 8 or sy < 8:
+                continue                                    # a sliver's centre lies inside the neighbour's filter footprint
+            w = part[b + oy + sy // 2, b + ox + sx // 2, 3]
+            assert (w > 0) == ((ox, oy) in mine), (r, ox, oy)
+    assert np.allclose(total, full, rtol=1e-6, atol=1e-6)
+
+
+def test_device_library_builds_the_same_tile_table():
+    """nb_debug_tile_order runs nb_api.cu's build_tile_order on the host (no device): the numbering nb_set_tiles / nb_render
+    shard by equals multigpu.tile_order for every group size and for ragged, single-row and single-tile grids."""
+    from nori_b200 import abi
+    for W, H in [(800, 600), (768, 768), (512, 512), (1920, 1080), (33, 1), (20, 20), (100, 700)]:
+        for world in range(1, 17):
+            assert abi.debug_tile_order(W, H, world) == MG.tile_order(W, H, world), (W, H, world)
