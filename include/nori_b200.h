@@ -242,6 +242,11 @@ int nb_debug_build_bvh(const float *verts4, const uint32_t *faces4, uint32_t npr
 /* Host-only diagnostic of the tile numbering (no context, no device): out[t] = bx | by << 16 of tile t for a group of
  * `nranks` (see nb_set_tiles); ceil(width/32) * ceil(height/32) entries.  Returns 0, 1 (bad argument) or 2 (capacity). */
 int nb_debug_tile_order(int width, int height, int nranks, uint32_t *bx_by_out, uint64_t cap);
+/* Host-only diagnostic of the work-unit schedule of one render launch (no context, no device): a rank that owns `n_tiles`
+ * tiles, `spp` samples per pixel, `resident_warps` = SMs x resident CTAs x 4, and the options chunk / guided / coarse of
+ * nb_set_option (guided < 0 = default).  out = { fine chunk, fine chunks per patch, first fine sample, coarse chunk, coarse
+ * chunks per patch, coarse units, units }.  Returns 0, 1 (bad argument) or 2 (more than 0xf0000000 units). */
+int nb_debug_unit_plan(int n_tiles, uint32_t spp, int64_t resident_warps, int64_t chunk, int64_t guided, int64_t coarse, uint32_t out[7]);
 /* Host-only diagnostic of the hierarchy cache: key -> load, else build + save, exactly as nb_build_accel does with
  * nb_set_accel_cache.  info = { nodes, leaf triangles, top nodes, depth, hit (0/1) }. */
 int nb_debug_bvh_cache(const float *verts4, const uint32_t *faces4, uint32_t nprims, int max_leaf, int64_t bfs_nodes, const char *path,

@@ -81,6 +81,7 @@ def lib():
         L.nb_debug_build_wide.argtypes = [vp, vp, u32, vp, u64, vp, u64, vp]
         L.nb_debug_wide_intersect.argtypes = [vp, u32, vp, vp, u64, i, vp, vp]
         L.nb_debug_tile_order.argtypes = [i, i, i, vp, u64]
+        L.nb_debug_unit_plan.argtypes = [i, u32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]
         L.nb_debug_bvh_cache.argtypes = [vp, vp, u32, i, C.c_int64, C.c_char_p, vp, u64, vp, u64, vp]
         L.nb_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i)]
         L.nb_set_camera.argtypes = [vp, vp, vp, i, i, f, f]
@@ -178,6 +179,15 @@ def debug_tile_order(width, height, nranks):
     if rc != 0:
         raise NoriError(f"nb_debug_tile_order failed ({rc})")
     return [(int(v & 0xffff), int(v >> 16)) for v in out]
+
+
+def debug_unit_plan(n_tiles, spp, resident_warps, chunk=0, guided=-1, coarse=0):
+    """nb_debug_unit_plan (no GPU): the work-unit schedule render_blocks hands the render kernel."""
+    out = np.zeros(7, dtype=np.uint32)
+    rc = lib().nb_debug_unit_plan(n_tiles, spp, resident_warps, chunk, guided, coarse, _p(out))
+    if rc != 0:
+        raise NoriError(f"nb_debug_unit_plan failed ({rc})")
+    return dict(zip(("chunk", "nchunks", "split_sample", "chunk_a", "nchunks_a", "split_units", "n_units"), (int(v) for v in out)))
 
 
 def debug_bvh_cache(V: np.ndarray, F: np.ndarray, path: str, max_leaf=3, bfs_nodes=2048):

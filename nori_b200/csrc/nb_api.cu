@@ -66,6 +66,43 @@ void build_tile_order(int ntx, int nty, int nranks, std::vector<uint32_t> &tab) 
     for (int r = 0; r < nranks; ++r) for (size_t q = 0; q < lists[(size_t) r].size(); ++q) tab[q * (size_t) nranks + (size_t) r] = lists[(size_t) r][q];
 }
 
+// Work units = (owned tile, 8x4 pixel patch, chunk of samples).  Chunk 8 renders 11 % faster than chunk 1 (a warp stays on its
+// 32 pixels, its walks share their nodes in L1) but a frame must END on small units, and a unit must stay a small part of
+// the frame (profiles/r2_call7_work_unit_size.txt, r2_call8_static_guided_ab.txt).  GUIDED schedule: the first `guided` percent
+// of the samples go in COARSE units -- the largest power of two <= 8 that still leaves >= 12 coarse units per resident warp
+// -- the rest in FINE units sized to leave >= 16 per warp.  Small shares (8 GPUs on the 9 ms frame) degenerate to the plain
+// fine schedule.  An explicit `chunk` option switches the schedule off.  Pure function of its arguments (nb_debug_unit_plan
+// runs it on the host); render_kernel decodes unit u as: u < split_units -> coarse (samples [0, split_sample) in chunks of
+// chunk_a), else fine (u - split_units; samples [split_sample, spp) in chunks of chunk); then patch = u % 32,
+// chunk id = (u / 32) % nchunks, tile slot = (u / 32) / nchunks.
+struct UnitPlan { uint32_t chunk, nchunks, split_sample, chunk_a, nchunks_a, split_units, n_units; };
+
+bool plan_units(int n_my_tiles, uint32_t spp, int64_t warps, int64_t opt_chunk, int64_t opt_guided, int64_t opt_coarse, UnitPlan &out) {
+    int64_t chunk = opt_chunk;
+    uint32_t split_sample = 0, coarse = 1;
+    if (chunk <= 0) {
+        const int64_t guided = std::max<int64_t>(0, std::min<int64_t>(100, opt_guided));
+        const int64_t want = opt_coarse > 0 ? opt_coarse : 8;
+        for (int64_t cc = want; cc >= 2 && !split_sample; cc /= 2) {
+            const uint32_t ss = (uint32_t) ((uint64_t) spp * (uint64_t) guided / 100 / (uint64_t) cc) * (uint32_t) cc;
+            if (ss >= (uint32_t) cc && (int64_t) n_my_tiles * 32 * (ss / cc) >= 12 * warps) { split_sample = ss; coarse = (uint32_t) cc; }
+        }
+        const int64_t units_fine = (int64_t) n_my_tiles * 32 * (spp - split_sample);
+        chunk = std::max<int64_t>(1, std::min<int64_t>(8, units_fine / (16 * warps)));
+        if (split_sample && chunk >= (int64_t) coarse) { split_sample = 0; chunk = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t) n_my_tiles * 32 * spp / (16 * warps))); }
+    }
+    const uint32_t spp_fine = spp - split_sample;
+    out.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t) std::max<uint32_t>(spp_fine, 1u)));
+    out.nchunks = spp_fine ? (spp_fine + out.chunk - 1) / out.chunk : 0;
+    out.split_sample = split_sample; out.chunk_a = coarse; out.nchunks_a = split_sample / coarse;
+    const unsigned long long units_a = (unsigned long long) n_my_tiles * 32ULL * out.nchunks_a;
+    const unsigned long long units = units_a + (unsigned long long) n_my_tiles * 32ULL * out.nchunks;
+    if (units > 0xf0000000ULL) return false;      // (+ one claim per warp past the end stays below 2^32)
+    out.split_units = (uint32_t) units_a;
+    out.n_units = (uint32_t) units;
+    return true;
+}
+
 int ensure_tile_table(nb_ctx *c, int nranks) {
     if (c->tile_tab_d && c->tab_W == c->W && c->tab_H == c->H && c->tab_N == nranks) return 0;
     const int ntx = (c->W + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE, nty = (c->H + NB_BLOCK_SIZE - 1) / NB_BLOCK_SIZE;
@@ -192,35 +229,10 @@ int render_blocks(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, i
     P.tile_tab = c->tile_tab_d;
     P.block_edge = NB_BLOCK_SIZE + 2 * c->border;
     if (P.block_edge > nb::kBlockEdgeMax) return fail("filter radius %.3f too large (border %d > 8)", c->fradius, c->border);
-    // Work units = (owned tile, 8x4 pixel patch, chunk of samples).  Chunk 8 renders 11 % faster than chunk 1 (a warp stays on its
-    // 32 pixels, its walks share their nodes in L1) but a frame must END on small units, and a unit must stay a small part of
-    // the frame (profiles/r2_call7_work_unit_size.txt, r2_call8_static_guided_ab.txt).  GUIDED schedule: the first `guided` percent
-    // of the samples go in COARSE units -- the largest power of two <= 8 that still leaves >= 12 coarse units per resident warp
-    // -- the rest in FINE units sized to leave >= 16 per warp.  Small shares (8 GPUs on the 9 ms frame) degenerate to the plain
-    // fine schedule.  An explicit `chunk` option switches the schedule off.
-    const int64_t warps = (int64_t) c->sm_count * NB_MIN_BLOCKS * 4;
-    int64_t chunk = c->opt_chunk;
-    uint32_t split_sample = 0, coarse = 1;
-    if (chunk <= 0) {
-        const int64_t guided = std::max<int64_t>(0, std::min<int64_t>(100, c->opt_guided));
-        const int64_t want = c->opt_coarse > 0 ? c->opt_coarse : 8;
-        for (int64_t cc = want; cc >= 2 && !split_sample; cc /= 2) {
-            const uint32_t ss = (uint32_t) ((uint64_t) spp * (uint64_t) guided / 100 / (uint64_t) cc) * (uint32_t) cc;
-            if (ss >= (uint32_t) cc && (int64_t) P.n_my_tiles * 32 * (ss / cc) >= 12 * warps) { split_sample = ss; coarse = (uint32_t) cc; }
-        }
-        const int64_t units_fine = (int64_t) P.n_my_tiles * 32 * (spp - split_sample);
-        chunk = std::max<int64_t>(1, std::min<int64_t>(8, units_fine / (16 * warps)));
-        if (split_sample && chunk >= (int64_t) coarse) { split_sample = 0; chunk = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t) P.n_my_tiles * 32 * spp / (16 * warps))); }
-    }
-    const uint32_t spp_fine = spp - split_sample;
-    P.chunk = (uint32_t) std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t) std::max<uint32_t>(spp_fine, 1u)));
-    P.nchunks = spp_fine ? (spp_fine + P.chunk - 1) / P.chunk : 0;
-    P.split_sample = split_sample; P.chunk_a = coarse; P.nchunks_a = split_sample / coarse;
-    const unsigned long long units_a = (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks_a;
-    const unsigned long long units = units_a + (unsigned long long) P.n_my_tiles * 32ULL * P.nchunks;
-    if (units > 0xf0000000ULL) return fail("too many work units");      // (+ one claim per warp past the end stays below 2^32)
-    P.split_units = (uint32_t) units_a;
-    P.n_units = (uint32_t) units;
+    UnitPlan plan;
+    if (!plan_units(P.n_my_tiles, spp, (int64_t) c->sm_count * NB_MIN_BLOCKS * 4, c->opt_chunk, c->opt_guided, c->opt_coarse, plan)) return fail("too many work units");
+    P.chunk = plan.chunk; P.nchunks = plan.nchunks; P.split_sample = plan.split_sample; P.chunk_a = plan.chunk_a; P.nchunks_a = plan.nchunks_a;
+    P.split_units = plan.split_units; P.n_units = plan.n_units;
     const size_t blk_elems = (size_t) P.n_my_tiles * P.block_edge * P.block_edge;
     if (!blocks_out) {
         if (blk_elems > c->blocks_cap) {
@@ -839,6 +851,15 @@ int nb_tile_count(nb_ctx *c, int rank, int nranks, int *ntiles, int *block_edge)
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("invalid tile shard (%d of %d)", rank, nranks);
     if (ntiles) *ntiles = tiles_for(c, rank, nranks, nullptr, nullptr);
     if (block_edge) *block_edge = NB_BLOCK_SIZE + 2 * c->border;
+    return 0;
+}
+
+// Host-only diagnostic (no context, no device): the work-unit plan of one render launch (plan_units above).
+int nb_debug_unit_plan(int n_tiles, uint32_t spp, int64_t resident_warps, int64_t chunk, int64_t guided, int64_t coarse, uint32_t out[7]) {
+    if (n_tiles < 0 || spp < 1 || resident_warps < 1 || !out) return 1;
+    UnitPlan p;
+    if (!plan_units(n_tiles, spp, resident_warps, chunk, guided < 0 ? 75 : guided, coarse, p)) return 2;
+    out[0] = p.chunk; out[1] = p.nchunks; out[2] = p.split_sample; out[3] = p.chunk_a; out[4] = p.nchunks_a; out[5] = p.split_units; out[6] = p.n_units;
     return 0;
 }
 

@@ -113,3 +113,52 @@ def test_device_library_builds_the_same_tile_table():
     for W, H in [(800, 600), (768, 768), (512, 512), (1920, 1080), (33, 1), (20, 20), (100, 700)]:
         for world in range(1, 17):
             assert abi.debug_tile_order(W, H, world) == MG.tile_order(W, H, world), (W, H, world)
+
+
+def _decode(plan, u):
+    """render_kernel's decode of work unit u (nb_kernels.cuh, regeneration loop) -> (tile slot, patch, first sample, samples)."""
+    if u < plan["split_units"]:
+        chunk, nchunks, s0 = plan["chunk_a"], plan["nchunks_a"], 0
+    else:
+        u -= plan["split_units"]
+        chunk, nchunks, s0 = plan["chunk"], plan["nchunks"], plan["split_sample"]
+    patch, rest = u % 32, u // 32
+    return rest // nchunks, patch, s0 + (rest % nchunks) * chunk, chunk
+
+
+def test_work_unit_plan_covers_every_sample_once():
+    """The guided schedule (nb_api.cu: plan_units, through nb_debug_unit_plan): whatever the options, the units of a launch
+    cover every (tile, patch, sample) exactly once, coarse units come first and stay inside [0, split_sample)."""
+    from nori_b200 import abi
+    B200 = 148 * 10 * 4
+    assert abi.debug_unit_plan(475, 64, B200) == dict(chunk=2, nchunks=8, split_sample=48, chunk_a=8, nchunks_a=6, split_units=475 * 32 * 6, n_units=475 * 32 * 14)
+    p = abi.debug_unit_plan(119, 64, B200)                                     # a rank of the 4-GPU headline frame
+    assert (p["chunk_a"], p["split_sample"], p["chunk"]) == (2, 48, 1)
+    p = abi.debug_unit_plan(60, 64, B200)                                      # ... of the 8-GPU frame: too little work for coarse units
+    assert (p["split_units"], p["chunk"], p["n_units"]) == (0, 1, 60 * 32 * 64)
+    assert abi.debug_unit_plan(2040, 4096, B200)["chunk"] == 8                  # configs[4]: 8 samples everywhere
+    with pytest.raises(abi.NoriError):
+        abi.debug_unit_plan(1 << 20, 1 << 20, B200, chunk=1)                   # > 0xf0000000 units
+    rng = np.random.default_rng(7)
+    cases = [(5, 13, 4, 0, -1, 0), (7, 64, 8, 0, 75, 8), (3, 100, 2, 0, 100, 8), (4, 37, 1, 0, 40, 4), (6, 64, 8, 0, 0, 0), (2, 9, 4, 3, -1, 0),
+             (1, 1, 4, 0, -1, 0), (0, 8, 4, 0, -1, 0), (9, 200, 16, 0, 75, 16), (3, 601, 3, 0, 1, 2)]
+    cases += [(int(rng.integers(1, 12)), int(rng.integers(1, 300)), int(rng.integers(1, 12)), int(rng.choice([0, 0, 0, 0, 1, 5, 64])),
+               int(rng.integers(-1, 101)), int(rng.choice([0, 2, 4, 8, 16]))) for _ in range(60)]
+    split_seen = 0
+    for n_tiles, spp, warps, chunk, guided, coarse in cases:
+        p = abi.debug_unit_plan(n_tiles, spp, warps, chunk, guided, coarse)
+        seen = np.zeros((max(n_tiles, 1), 32, spp), dtype=np.int32)
+        for u in range(p["n_units"]):
+            slot, patch, s0, ns = _decode(p, u)
+            assert slot < n_tiles
+            s1 = min(s0 + ns, spp)                                               # the kernel clips the last chunk to spp
+            if u < p["split_units"]:
+                assert s1 <= p["split_sample"]
+            else:
+                assert s0 >= p["split_sample"]
+            seen[slot, patch, s0:s1] += 1
+        assert p["n_units"] == 0 if n_tiles == 0 else np.all(seen == 1), (n_tiles, spp, warps, chunk, guided, coarse, p)
+        split_seen += p["split_units"] > 0
+        if chunk > 0:
+            assert p["split_units"] == 0 and p["chunk"] == min(chunk, spp)
+    assert split_seen >= 10                                                       # the coarse / fine split was exercised
