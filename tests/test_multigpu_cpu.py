@@ -162,3 +162,29 @@ def test_work_unit_plan_covers_every_sample_once():
         if chunk > 0:
             assert p["split_units"] == 0 and p["chunk"] == min(chunk, spp)
     assert split_seen >= 10                                                       # the coarse / fine split was exercised
+
+
+def test_tile_table_properties_for_arbitrary_frames():
+    """Property test (hypothesis): for any frame and group size the table is a permutation of the tile grid, the ranks' counts
+    differ by at most one, rank r owns tiles r, r + N, ..., and no rank owns a whole column of a grid it could share."""
+    from hypothesis import given, settings, strategies as st
+    from nori_b200 import abi
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(1, 2200), st.integers(1, 1300), st.integers(1, 16))
+    def check(W, H, world):
+        order = abi.debug_tile_order(W, H, world)
+        ntx, nty = MG.tile_grid(W, H)
+        assert sorted(order) == [(bx, by) for bx in range(ntx) for by in range(nty)]
+        assert order == MG.tile_order(W, H, world)
+        counts = [len(range(r, len(order), world)) for r in range(world)]
+        assert max(counts) - min(counts) <= 1
+        if world > 1 and ntx >= world and nty >= world:
+            for r in range(world):
+                cols = {}
+                for bx, by in order[r::world]:
+                    cols[bx] = cols.get(bx, 0) + 1
+                assert max(cols.values()) < nty, (W, H, world, r)
+    check()
+    with pytest.raises(abi.NoriError):
+        abi.debug_tile_order(0, 10, 2)
