@@ -431,7 +431,6 @@ int render_tiles(nb_ctx *c, float4 *blocks_out, cudaStream_t s, nb_stats *st, in
 
 int merge(nb_ctx *c, const float4 *blocks, int n_tiles, int rank, int nranks, float4 *film, cudaStream_t s) {
     if (n_tiles <= 0) return 0;
-    int ntx = (c->W + 31) / 32;
     int edge = NB_BLOCK_SIZE + 2 * c->border;
     long long total = (long long) n_tiles * edge * edge;
     int grid = (int) ((total + 255) / 256);
